@@ -1,0 +1,96 @@
+/* B200-specific additions to the C ABI (everything the reference header cannot express):
+ * device-resident factor / solve entry points, 64-bit counters, table getters used by the
+ * parity tests, stream control for event timing, and the multi-GPU hooks.
+ *
+ * Plain pointers and sizes only.  `d_` arguments are device pointers on the current CUDA
+ * device; `stream` is a cudaStream_t passed as void* (NULL = the library's own stream).
+ */
+#ifndef SPLLT_B200_H
+#define SPLLT_B200_H
+
+#include "spllt_iface.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ordering selector for spllt_b200_analyse (the reference always uses METIS,
+ * src/spllt_analyse_mod.F90:109): 1 = METIS nested dissection, 0 = natural, 2 = `order` is input */
+void spllt_b200_analyse(void **akeep, void **fkeep, spllt_options_t *options, int n, const int *ptr,
+                        const int *row, spllt_inform_t *info, int *order, int ordering);
+
+/* ---- 64-bit counters (spllt_inform_t truncates, interfaces/C/spllt_data_ciface.F90:77-78) */
+long long spllt_b200_num_factor(void *akeep);   /* entries of L                                */
+long long spllt_b200_num_flops(void *akeep);    /* akeep%weight(nnodes+1), analyse_mod:1013-1021 */
+long long spllt_b200_arena_doubles(void *akeep); /* HBM arena size                              */
+int spllt_b200_num_nodes(void *akeep);
+int spllt_b200_num_bcol(void *akeep);
+long long spllt_b200_final_blk(void *akeep);
+int spllt_b200_maxmn(void *akeep);
+int spllt_b200_num_depth(void *akeep);          /* block-column level sets in the schedule     */
+
+/* ---- symbolic tables, reference numbering (1-based), for bit-exact comparison
+ * sptr[nnodes+1], sparent[nnodes], rptr[nnodes+1] (64-bit), rlist[rptr[nnodes]-1] */
+void spllt_b200_get_symbolic(void *akeep, int *sptr, int *sparent, long long *rptr, int *rlist);
+long long spllt_b200_rlist_len(void *akeep);
+/* 9 columns per tile: id blkm blkn sa dblk last_blk node bcol dep_initial (spllt_block) */
+void spllt_b200_get_blocks(void *akeep, long long *out);
+/* 8 columns per node: sa en parent nchild least_desc nb blk_sa blk_en (spllt_node) */
+void spllt_b200_get_nodes(void *akeep, long long *out);
+void spllt_b200_get_small(void *akeep, int *out);          /* akeep%small(1:nnodes)  */
+void spllt_b200_get_weight(void *akeep, long long *out);   /* akeep%weight(1:nnodes+1) */
+long long spllt_b200_lmap_len(void *akeep, int bcol);      /* bcol 1-based */
+void spllt_b200_get_lmap(void *akeep, int bcol, long long *dst, long long *src); /* lmap(bcol)%map(1:2,:) */
+/* solve tiles of get_solve_blocks (src/spllt_solve_dep_mod.F90:1861-2030):
+ * 9 columns: id blkm blkn sa dblk last_blk bcol node ldu */
+int spllt_b200_num_sblocks(void *akeep, int nb);
+void spllt_b200_get_sblocks(void *akeep, int nb, int *out);
+
+/* ---- factor entries in the reference layout (lfact(bcol)%lcol, row-major tiles) */
+long long spllt_b200_lcol_size(void *akeep, int bcol);
+void spllt_b200_get_lcol(void *fkeep, int bcol, double *out);   /* device -> host, synchronises */
+long long spllt_b200_factor_size(void *akeep);
+void spllt_b200_get_factor(void *fkeep, double *out);
+
+/* ---- device-resident hot path */
+void spllt_b200_set_stream(void *fkeep, void *stream);
+/* d_val: the user's val array already in HBM (nnz doubles).  Asynchronous on the stream. */
+void spllt_b200_factor_dev(void *akeep, void *fkeep, const double *d_val, spllt_inform_t *info);
+/* d_x: n x nrhs column-major (ldx >= n) in HBM, overwritten.  Asynchronous on the stream. */
+void spllt_b200_solve_dev(void *fkeep, int nrhs, double *d_x, int ldx, int job, spllt_inform_t *info);
+/* forward result of job 1 in pivot order, n x nrhs row-major -> host (synchronises) */
+void spllt_b200_get_fwd(void *fkeep, int nrhs, double *out);
+/* reads the device pivot flag (synchronises): 0 = ok, else 1-based pivot column that failed */
+int spllt_b200_pivot_flag(void *fkeep);
+
+/* spllt_chkerr without printing: err[nrhs] receives the scaled backward errors
+ * (src/utils_mod.F90:432-478); returns how many are <= 1e-14 */
+int spllt_b200_chkerr(int n, const int *ptr, const int *row, const double *val, int nrhs, const double *x,
+                      const double *rhs, double *err);
+
+/* ---- counters for bench.py */
+long long spllt_b200_factor_launches(void *fkeep);  /* kernels per spllt_factor             */
+long long spllt_b200_solve_launches(void *fkeep, int job);
+double spllt_b200_tile_flops(void *akeep);          /* flops issued by the DMMA tile kernels */
+/* per-kernel-kind launch counts of one factorization: potrf, trsm, tile_s, tile_l */
+void spllt_b200_launch_breakdown(void *akeep, long long *out4);
+
+/* ---- FP64 peak probes (no FP64 figure in MEASURED_PEAKS.json): enqueue a register-resident
+ * DMMA (kind 0) or DFMA (kind 1) loop on every SM; returns the flops it will execute */
+double spllt_b200_peak_probe(int kind, int iters, void *stream);
+
+/* ---- multi-GPU hooks (one process per GPU; collectives are done by the caller on arena
+ * slices, e.g. torch.distributed over NCCL) */
+void *spllt_b200_arena_ptr(void *fkeep);            /* device pointer of the HBM arena        */
+/* node ownership: rank r factorizes the subtrees given to it by proportional mapping; nodes
+ * above the split are "shared" (owner -1) and factorized by every rank after the reduction */
+void spllt_b200_partition(void *akeep, void *fkeep, int rank, int world);
+/* [begin, end) offsets (doubles) of the shared top-of-tree region in the arena */
+void spllt_b200_shared_region(void *akeep, long long *begin, long long *end);
+/* phase 0 = assemble + local subtrees, phase 1 = shared top; both asynchronous */
+void spllt_b200_factor_phase(void *akeep, void *fkeep, const double *d_val, int phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

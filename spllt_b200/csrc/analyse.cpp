@@ -1,0 +1,509 @@
+// Host analysis of the B200 build: everything spllt_analyse does after the ordering /
+// symbolic factorization (src/spllt_analyse_mod.F90:210-558), re-expressed as flat tables,
+// plus the value-independent schedules that replace the run-time task DAG:
+//   * closed-form tile table (what :338-469 builds with nested counters),
+//   * A -> L scatter map (:1033-1171),
+//   * tree pruning (:806-987) -- also reused as the subtree -> GPU partitioner,
+//   * block-column level sets + tile work lists for the factorization (replaces
+//     src/spllt_factorization_mod.F90:474-751 unrolling tasks at run time),
+//   * inter-node update maps (replaces update_between_compute_map being recomputed per
+//     task, src/spllt_kernels_mod.F90:1606-1723),
+//   * level sets for the triangular solves (replaces src/spllt_solve_dep_mod.F90).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+
+#include "model.h"
+
+namespace spllt {
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline i64 rup(i64 a, i64 b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------
+// Heap sort of (key, tag) pairs into ascending key order.  The pruning heuristic depends on
+// how ties are permuted, so this is the same textbook sift-down variant the reference uses
+// (src/spllt_utils_mod.F90:22-140): right child only if strictly larger, stop on <=.
+static void sift(std::vector<i64>& key, std::vector<int>& tag, int root, int last) {
+  i64 k = key[root];
+  int t = tag[root];
+  int hole = root;
+  for (int ch = 2 * hole + 1; ch <= last; ch = 2 * hole + 1) {
+    if (ch < last && key[ch + 1] > key[ch]) ++ch;
+    if (key[ch] <= k) break;
+    key[hole] = key[ch];
+    tag[hole] = tag[ch];
+    hole = ch;
+  }
+  key[hole] = k;
+  tag[hole] = t;
+}
+static void heap_sort(std::vector<i64>& key, std::vector<int>& tag, int cnt) {
+  if (cnt <= 1) return;
+  for (int r = cnt / 2 - 1; r >= 0; --r) sift(key, tag, r, cnt - 1);
+  for (int i = cnt - 1; i >= 1; --i) {
+    std::swap(key[0], key[i]);
+    std::swap(tag[0], tag[i]);
+    sift(key, tag, 0, i - 1);
+  }
+}
+
+// Tree pruning (src/spllt_analyse_mod.F90:806-987).  Nodes are 0-based, the virtual root is
+// node `nnodes`.  small[] uses the reference's encoding (1 = subtree root, -(root+1) =
+// inside that subtree, 0 = upper tree) so it can be compared with akeep%small directly.
+void prune_tree(Analysis& A, int nth, std::vector<int>& small) {
+  const int nn = A.nnodes;
+  small.assign(nn, 0);
+  if (nn == 0) return;
+  if (nth < 1) nth = 1;
+  // children lists (ascending), including those of the virtual root
+  std::vector<int> cptr(nn + 2, 0), clist(nn);
+  for (int s = 0; s < nn; ++s) cptr[(A.nodes[s].parent < 0 ? nn : A.nodes[s].parent) + 1]++;
+  for (int s = 0; s <= nn; ++s) cptr[s + 1] += cptr[s];
+  {
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int s = 0; s < nn; ++s) clist[fill[A.nodes[s].parent < 0 ? nn : A.nodes[s].parent]++] = s;
+  }
+  int totleaves = 0;
+  for (int s = 0; s <= nn; ++s)
+    if (cptr[s + 1] == cptr[s]) ++totleaves;
+  const i64 total = A.weight[nn];
+  const double cap = (double)nth * std::max(2.0, std::pow(std::log((double)nth) / std::log(2.0), 2));
+  auto mark = [&](int c) {
+    for (int k = A.nodes[c].least_desc; k <= c; ++k) small[k] = -(c + 1);
+    small[c] = 1;
+  };
+  std::vector<i64> key(nn + 1), load(nth);
+  std::vector<int> layer(nn + 1);
+  int cnt = 0;
+  // the reference assigns default-real literals to double variables (:840, :903)
+  for (double thr = (double)0.01f;; thr /= 2.0) {
+    std::fill(small.begin(), small.end(), 0);
+    cnt = 1;
+    layer[0] = nn;
+    key[0] = -total;
+    int stuck = 0;  // entries of the layer known to have no child above the threshold
+    bool again = false;
+    for (;;) {
+      if (cnt <= 0 || (double)cnt > cap) break;
+      heap_sort(key, layer, cnt);
+      std::fill(load.begin(), load.end(), 0);
+      for (int i = 0; i < cnt; ++i) *std::min_element(load.begin(), load.end()) += std::llabs(key[i]);
+      float bal = (float)*std::min_element(load.begin(), load.end()) /
+                  (float)*std::max_element(load.begin(), load.end());
+      if ((double)bal > (double)0.9f && cnt >= nth) break;
+      bool grew = false, done = false;
+      while (!grew) {
+        if (stuck == totleaves) { done = true; break; }
+        if (stuck == cnt) {
+          if ((double)cnt >= cap || thr / 2.0 < (double)1e-4f) done = true;
+          else again = true;
+          break;
+        }
+        int v = layer[stuck];
+        for (int q = cptr[v]; q < cptr[v + 1]; ++q) {
+          int c = clist[q];
+          if ((double)A.weight[c] > thr * (double)total) {
+            grew = true;
+            layer[cnt] = c;
+            key[cnt] = -A.weight[c];
+            ++cnt;
+          } else {
+            mark(c);
+          }
+        }
+        if (!grew) ++stuck;
+      }
+      if (done || again) break;
+      layer[stuck] = layer[cnt - 1];
+      key[stuck] = key[cnt - 1];
+      --cnt;
+    }
+    if (!again) break;
+  }
+  for (int i = 0; i < cnt; ++i)
+    for (int q = cptr[layer[i]]; q < cptr[layer[i] + 1]; ++q) mark(clist[q]);
+}
+
+// ------------------------------------------------------------------------------------------
+int build_analysis(int n, const int* ptr, const int* row, int nb, int nemin, int ncpu, int prune,
+                   int ordering, const int* user_order, Analysis& A) {
+  A = Analysis();
+  A.n = n;
+  A.nb = nb < 1 ? 256 : nb;  // nb_default, src/spllt_data_mod.F90:39, src/spllt_analyse_mod.F90:316
+  A.nemin = nemin;
+  A.ncpu = ncpu < 1 ? 1 : ncpu;
+  A.prune = prune;
+  if (n <= 0) return 0;
+  A.nnz = (i64)ptr[n] - 1;
+  int rc = symbolic_analyse(n, ptr, row, nemin, ordering, user_order, A.sym);
+  if (rc) return rc;
+  const Symbolic& S = A.sym;
+  const int nn = A.nnodes = S.nnodes;
+  nb = A.nb;
+
+  A.porder.resize(n);
+  for (int v = 0; v < n; ++v) A.porder[S.order[v] - 1] = v;
+
+  A.nodes.resize(nn);
+  A.index.resize(S.rlist.size());
+  for (size_t k = 0; k < S.rlist.size(); ++k) A.index[k] = S.rlist[k] - 1;
+  A.col2node.resize(n);
+  A.weight.assign(nn + 1, 0);
+  i64 blk = 0, off = 0, rowbase = 0, nfac = 0;
+  int bcol = 0;
+  A.maxmn = 0;
+  for (int s = 0; s < nn; ++s) {
+    HNode& nd = A.nodes[s];
+    nd.sa = S.sptr[s] - 1;
+    nd.en = S.sptr[s + 1] - 2;
+    nd.n = nd.en - nd.sa + 1;
+    nd.m = (int)(S.rptr[s + 1] - S.rptr[s]);
+    nd.idx_off = S.rptr[s] - 1;
+    nd.parent = S.sparent[s] > nn ? -1 : S.sparent[s] - 1;
+    nd.nchild = 0;
+    nd.least_desc = s;
+    nd.nc = cdiv(nd.n, nb);
+    nd.nr = cdiv(nd.m, nb);
+    nd.bcol0 = bcol;
+    nd.blk0 = blk;
+    nd.small = 0;
+    nd.owner = 0;
+    nd.ld = (int)rup(nd.n, LDPAD);
+    nd.off = 0;
+    nd.row_base = rowbase;
+    rowbase += nd.m - nd.n;
+    bcol += nd.nc;
+    // sum_{c<nc} (nr - c) tiles
+    blk += (i64)nd.nc * nd.nr - (i64)nd.nc * (nd.nc - 1) / 2;
+    for (int c = nd.sa; c <= nd.en; ++c) A.col2node[c] = s;
+    // flops of the node, src/spllt_analyse_mod.F90:1013-1018
+    i64 mm = nd.m - nd.n, f = 0;
+    for (i64 j = 1; j <= nd.n; ++j) f += (mm + j) * (mm + j);
+    A.weight[s] += f;
+    A.weight[nd.parent < 0 ? nn : nd.parent] += A.weight[s];
+    nfac += (i64)nd.n * nd.m - (i64)nd.n * (nd.n - 1) / 2;
+    A.maxmn = std::max(A.maxmn, std::min(nb, nd.m));
+  }
+  A.nbcol = bcol;
+  A.final_blk = blk;
+  A.num_flops = A.weight[nn];
+  A.num_factor = nfac;
+  for (int s = 0; s < nn; ++s) {
+    int p = A.nodes[s].parent;
+    if (p >= 0) {
+      A.nodes[p].nchild++;
+      A.nodes[p].least_desc = std::min(A.nodes[p].least_desc, A.nodes[s].least_desc);
+    }
+  }
+  std::vector<int> small;
+  if (prune) {
+    prune_tree(A, A.ncpu, small);
+    for (int s = 0; s < nn; ++s) A.nodes[s].small = small[s];
+  }
+  // Arena layout: pruned subtrees first, the upper tree (small == 0) last, so that the part
+  // of L that several GPUs contribute to is one contiguous slice (multi-GPU reduction).
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) A.top_begin = off;
+    for (int s = 0; s < nn; ++s) {
+      HNode& nd = A.nodes[s];
+      if ((nd.small == 0) != (pass == 1)) continue;
+      nd.off = off;
+      off += rup((i64)nd.m * nd.ld, 16);
+    }
+  }
+  A.arena = off;
+
+  // block column -> node table
+  A.bcol_node.resize(A.nbcol);
+  A.bcol_c.resize(A.nbcol);
+  for (int s = 0; s < nn; ++s)
+    for (int c = 0; c < A.nodes[s].nc; ++c) {
+      A.bcol_node[A.nodes[s].bcol0 + c] = s;
+      A.bcol_c[A.nodes[s].bcol0 + c] = c;
+    }
+
+  // ---- A -> L map.  Entry (i, j) of the user's lower triangle lands in pivot column
+  // min(p_i, p_j), pivot row max(p_i, p_j); per pivot column the entries keep the order in
+  // which a scan of the user's columns meets them (what spllt_make_map's bucket pass yields).
+  {
+    std::vector<i64> cnt(n + 1, 0);
+    for (int j = 0; j < n; ++j) {
+      int pj = S.order[j] - 1;
+      for (i64 e = ptr[j] - 1; e < ptr[j + 1] - 1; ++e) cnt[std::min(pj, S.order[row[e] - 1] - 1) + 1]++;
+    }
+    for (int c = 0; c < n; ++c) cnt[c + 1] += cnt[c];
+    std::vector<i64> colptr(cnt);
+    std::vector<int> prow(A.nnz);
+    std::vector<i64> psrc(A.nnz);
+    for (int j = 0; j < n; ++j) {
+      int pj = S.order[j] - 1;
+      for (i64 e = ptr[j] - 1; e < ptr[j + 1] - 1; ++e) {
+        int pi = S.order[row[e] - 1] - 1;
+        i64 slot = cnt[std::min(pi, pj)]++;
+        prow[slot] = std::max(pi, pj);
+        psrc[slot] = e;
+      }
+    }
+    A.lmap_ptr.assign(A.nbcol + 1, 0);
+    A.lmap_row.resize(A.nnz);
+    A.lmap_col.resize(A.nnz);
+    A.lmap_src.resize(A.nnz);
+    std::vector<int> where(n, -1);  // pivot row -> row position in the current node
+    i64 w = 0;
+    for (int s = 0; s < nn; ++s) {
+      const HNode& nd = A.nodes[s];
+      const int* idx = A.index.data() + nd.idx_off;
+      for (int r = 0; r < nd.m; ++r) where[idx[r]] = r;
+      for (int c = 0; c < nd.nc; ++c) {
+        int c0 = nd.sa + c * nb, c1 = std::min(c0 + nb - 1, nd.en);
+        for (int col = c0; col <= c1; ++col)
+          for (i64 e = colptr[col]; e < colptr[col + 1]; ++e) {
+            int r = where[prow[e]];
+            if (r < 0) return -3;  // entry outside the symbolic pattern
+            A.lmap_row[w] = r;
+            A.lmap_col[w] = col - nd.sa;
+            A.lmap_src[w] = psrc[e];
+            ++w;
+          }
+        A.lmap_ptr[nd.bcol0 + c + 1] = w;
+      }
+      for (int r = 0; r < nd.m; ++r) where[idx[r]] = -1;
+    }
+  }
+
+  // ---- schedule depth of block columns: (s, c) runs after (s, c-1) and after every child
+  int ndepth = 0;
+  for (int s = 0; s < nn; ++s) A.nodes[s].depth0 = 0;
+  for (int s = 0; s < nn; ++s) {
+    HNode& nd = A.nodes[s];
+    int last = nd.depth0 + nd.nc - 1;
+    ndepth = std::max(ndepth, last + 1);
+    if (nd.parent >= 0) A.nodes[nd.parent].depth0 = std::max(A.nodes[nd.parent].depth0, last + 1);
+  }
+  A.ndepth = ndepth;
+  return 0;
+}
+
+// Closed form of the tile table that src/spllt_analyse_mod.F90:381-469 fills with running
+// counters.  Tile r (block row, c <= r < nr) of block column c of a node.
+void ref_blocks(const Analysis& A, std::vector<RefBlock>& out) {
+  out.resize(A.final_blk);
+  const int nb = A.nb;
+  for (int s = 0; s < A.nnodes; ++s) {
+    const HNode& nd = A.nodes[s];
+    i64 id = nd.blk0;
+    for (int c = 0; c < nd.nc; ++c) {
+      i64 dblk = id + 1;
+      int blkn = std::min(nb, nd.n - c * nb);
+      for (int r = c; r < nd.nr; ++r, ++id) {
+        RefBlock& b = out[id];
+        b.id = id + 1;
+        b.blkm = std::min(nb, nd.m - r * nb);
+        b.blkn = blkn;
+        b.sa = 1 + (i64)(r - c) * nb * blkn;
+        b.dblk = dblk;
+        b.last_blk = dblk + (nd.nr - c) - 1;
+        b.node = s + 1;
+        b.bcol = nd.bcol0 + c + 1;
+        b.dep_initial = (r == c) ? c : c + 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Factorization schedule.
+//
+// Depth d holds every block column (s, c) with depth0(s) + c == d.  Inside a depth all block
+// columns advance together through their inner panels (width IB):
+//   potrf(panel diag) -> trsm(rows below) -> tile update of the rest of the block column
+// then one "outer" launch group applies the finished block columns to
+//   * the later block columns of the same node (a3, K = width of the block column), and
+//   * if the node is complete, to its ancestors (a4, K = n, scatter through q_* maps).
+static void add_tiles(Analysis& A, std::vector<TileTask>& small, std::vector<TileTask>& large,
+                      const HNode& nd, int jbeg, int jend, int ibeg_min, int iend, int k0, int kk,
+                      int src, int tile_l_min) {
+  // region: columns (B rows) j in [jbeg, jend), rows i in [max(j, ibeg_min), iend), lower part
+  if (jend <= jbeg || iend <= jbeg) return;
+  i64 area = (i64)(jend - jbeg) * (iend - std::max(jbeg, ibeg_min));
+  bool big = (jend - jbeg) >= tile_l_min && (iend - jbeg) >= tile_l_min && area >= (i64)128 * 128 && kk >= 16;
+  const int T = big ? 128 : 64;
+  std::vector<TileTask>& dst = big ? large : small;
+  for (int j0 = jbeg; j0 < jend; j0 += T) {
+    int nt = std::min(T, jend - j0);
+    int istart = std::max(j0, ibeg_min);
+    for (int i0 = istart; i0 < iend; i0 += T) {
+      TileTask t;
+      t.off = nd.off;
+      t.ld = nd.ld;
+      t.i0 = i0;
+      t.j0 = j0;
+      t.k0 = k0;
+      t.mt = std::min(T, iend - i0);
+      t.nt = nt;
+      t.kk = kk;
+      t.src = src;
+      t.qoff = nd.row_base - nd.n;
+      dst.push_back(t);
+      A.tile_flops += 2.0 * T * T * kk;
+    }
+  }
+}
+
+void build_factor_schedule(Analysis& A, int tile_l_min) {
+  const int nn = A.nnodes, nb = A.nb;
+  A.potrf_tasks.clear();
+  A.trsm_tasks.clear();
+  A.tile_tasks.clear();
+  A.launches.clear();
+  A.tile_flops = 0;
+
+  // ---- inter-node update maps
+  i64 nrows = 0;
+  for (int s = 0; s < nn; ++s) nrows += A.nodes[s].m - A.nodes[s].n;
+  A.q_base.assign(nrows, 0);
+  A.q_ld.assign(nrows, 0);
+  A.q_rp.assign(nrows, 0);
+  A.rowpos.clear();
+  for (int s = 0; s < nn; ++s) {
+    const HNode& nd = A.nodes[s];
+    const int* idx = A.index.data() + nd.idx_off;
+    int r = nd.n;
+    while (r < nd.m) {
+      int a = A.col2node[idx[r]];
+      const HNode& an = A.nodes[a];
+      int r1 = r;
+      while (r1 < nd.m && idx[r1] <= an.en) ++r1;
+      // rows [r, r1) are columns of ancestor a; rows [r, m) are all rows of a
+      i64 rp = (i64)A.rowpos.size() - r;
+      const int* aidx = A.index.data() + an.idx_off;
+      int pa = idx[r] - an.sa;  // rows of a start with its own columns in order
+      for (int q = r; q < nd.m; ++q) {
+        while (aidx[pa] != idx[q]) ++pa;
+        A.rowpos.push_back(pa);
+      }
+      for (int q = r; q < r1; ++q) {
+        i64 g = nd.row_base + (q - nd.n);
+        A.q_base[g] = an.off + (idx[q] - an.sa);
+        A.q_ld[g] = an.ld;
+        A.q_rp[g] = rp;
+      }
+      r = r1;
+    }
+  }
+
+  // ---- level sets
+  std::vector<std::vector<int>> at(A.ndepth);  // global block-column ids per depth
+  for (int s = 0; s < nn; ++s)
+    for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
+
+  std::vector<TileTask> ts, tl;
+  auto flush_tiles = [&](int depth) {
+    if (!ts.empty()) {
+      A.launches.push_back({L_TILE_S, depth, (i64)A.tile_tasks.size(), (i64)ts.size()});
+      A.tile_tasks.insert(A.tile_tasks.end(), ts.begin(), ts.end());
+      ts.clear();
+    }
+    if (!tl.empty()) {
+      A.launches.push_back({L_TILE_L, depth, (i64)A.tile_tasks.size(), (i64)tl.size()});
+      A.tile_tasks.insert(A.tile_tasks.end(), tl.begin(), tl.end());
+      tl.clear();
+    }
+  };
+
+  for (int d = 0; d < A.ndepth; ++d) {
+    int maxsteps = 0;
+    for (int g : at[d]) {
+      const HNode& nd = A.nodes[A.bcol_node[g]];
+      int w = std::min(nb, nd.n - A.bcol_c[g] * nb);
+      maxsteps = std::max(maxsteps, cdiv(w, IB));
+    }
+    for (int p = 0; p < maxsteps; ++p) {
+      i64 p0 = A.potrf_tasks.size(), t0 = A.trsm_tasks.size();
+      for (int g : at[d]) {
+        const HNode& nd = A.nodes[A.bcol_node[g]];
+        int r0 = A.bcol_c[g] * nb;
+        int w = std::min(nb, nd.n - r0);
+        if (p * IB >= w) continue;
+        int pw = std::min(IB, w - p * IB);
+        int k0 = r0 + p * IB;
+        PanelTask pt;
+        pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
+        pt.ld = nd.ld;
+        pt.pw = pw;
+        pt.col0 = nd.sa + k0;
+        pt.pad = 0;
+        A.potrf_tasks.push_back(pt);
+        for (int r = k0 + pw; r < nd.m; r += TRSM_ROWS) {
+          TrsmTask tt;
+          tt.d_off = pt.d_off;
+          tt.r_off = nd.off + (i64)r * nd.ld + k0;
+          tt.ld = nd.ld;
+          tt.pw = pw;
+          tt.nrows = std::min(TRSM_ROWS, nd.m - r);
+          tt.pad = 0;
+          A.trsm_tasks.push_back(tt);
+        }
+        // rest of this block column
+        add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+      }
+      if ((i64)A.potrf_tasks.size() > p0)
+        A.launches.push_back({L_POTRF, d, p0, (i64)A.potrf_tasks.size() - p0});
+      if ((i64)A.trsm_tasks.size() > t0)
+        A.launches.push_back({L_TRSM, d, t0, (i64)A.trsm_tasks.size() - t0});
+      flush_tiles(d);
+    }
+    // outer updates of the block columns finished at this depth
+    for (int g : at[d]) {
+      const HNode& nd = A.nodes[A.bcol_node[g]];
+      int c = A.bcol_c[g];
+      int r0 = c * nb;
+      int w = std::min(nb, nd.n - r0);
+      if (c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
+      if (c + 1 == nd.nc && nd.m > nd.n)
+        add_tiles(A, ts, tl, nd, nd.n, nd.m, 0, nd.m, 0, nd.n, A.bcol_node[g], tile_l_min);
+    }
+    flush_tiles(d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Solve schedule: the same block-column level sets.  Forward: diag solve of the block
+// column, then x[index[r]] -= L[r, bcol] * x_bcol for the rows below.  Backward: the reverse.
+void build_solve_schedule(Analysis& A) {
+  const int nn = A.nnodes, nb = A.nb;
+  A.sbcols.clear();
+  A.supds.clear();
+  A.slaunch.assign(A.ndepth, SolveLaunch{0, 0, 0, 0});
+  std::vector<std::vector<int>> at(A.ndepth);
+  for (int s = 0; s < nn; ++s)
+    for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
+  for (int d = 0; d < A.ndepth; ++d) {
+    SolveLaunch& L = A.slaunch[d];
+    L.diag_begin = A.sbcols.size();
+    L.upd_begin = A.supds.size();
+    for (int g : at[d]) {
+      const HNode& nd = A.nodes[A.bcol_node[g]];
+      SolveBcol b;
+      b.off = nd.off;
+      b.idx_off = nd.idx_off;
+      b.ld = nd.ld;
+      b.m = nd.m;
+      b.r0 = A.bcol_c[g] * nb;
+      b.w = std::min(nb, nd.n - b.r0);
+      b.sa = nd.sa;
+      b.pad = 0;
+      int id = (int)A.sbcols.size();
+      A.sbcols.push_back(b);
+      for (int r = b.r0 + b.w; r < nd.m; r += SOLVE_ROWS)
+        A.supds.push_back({id, r, std::min(SOLVE_ROWS, nd.m - r), 0});
+    }
+    L.diag_count = (i64)A.sbcols.size() - L.diag_begin;
+    L.upd_count = (i64)A.supds.size() - L.upd_begin;
+  }
+}
+
+}  // namespace spllt

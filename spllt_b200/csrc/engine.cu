@@ -1,0 +1,271 @@
+// Device-side state of one analysed matrix: HBM arena, uploaded work lists, captured CUDA
+// graphs.  Replaces spllt_fkeep's lfact(:) / workspaces (src/spllt_data_mod.F90:330-388,
+// src/spllt_factorization_mod.F90:347-472) and the STF / task-manager drivers
+// (src/spllt_stf_mod.F90:18-192, src/spllt_solve_mod.F90:244-411).
+#include "engine.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace spllt {
+
+#define CK(x)                                                                                            \
+  do {                                                                                                   \
+    cudaError_t e_ = (x);                                                                                \
+    if (e_ != cudaSuccess) {                                                                             \
+      fprintf(stderr, "spllt_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      abort();                                                                                           \
+    }                                                                                                    \
+  } while (0)
+
+template <class T>
+static T* upload(const std::vector<T>& v) {
+  T* d = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CK(cudaMalloc(&d, bytes));
+  if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+static bool g_kernels_ready = false;
+
+void require_gpu() {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    fprintf(stderr,
+            "spllt_b200: no CUDA device available -- the numerical phase has no CPU fallback "
+            "(cudaGetDeviceCount: %s)\n",
+            cudaGetErrorString(e));
+    abort();
+  }
+}
+
+void Engine::upload_tables() {
+  if (uploaded) return;
+  require_gpu();
+  if (!g_kernels_ready) {
+    kernels_init();
+    g_kernels_ready = true;
+  }
+  CK(cudaGetDevice(&device));
+  const Analysis& S = *A;
+  if (!own_stream) {
+    CK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    own_stream = true;
+  }
+  if (!stream) stream = own;
+  CK(cudaMalloc(&arena, std::max<i64>(S.arena, 1) * sizeof(double)));
+  CK(cudaMemset(arena, 0, std::max<i64>(S.arena, 1) * sizeof(double)));
+  // A -> L map with arena addresses
+  {
+    std::vector<i64> dst(S.nnz);
+    for (int g = 0; g < S.nbcol; ++g) {
+      const HNode& nd = S.nodes[S.bcol_node[g]];
+      for (i64 e = S.lmap_ptr[g]; e < S.lmap_ptr[g + 1]; ++e)
+        dst[e] = nd.off + (i64)S.lmap_row[e] * nd.ld + S.lmap_col[e];
+    }
+    d_lmap_dst = upload(dst);
+    d_lmap_src = upload(S.lmap_src);
+  }
+  CK(cudaMalloc(&d_val, std::max<i64>(S.nnz, 1) * sizeof(double)));
+  d_potrf = upload(S.potrf_tasks);
+  d_trsm = upload(S.trsm_tasks);
+  d_tile = upload(S.tile_tasks);
+  d_qbase = upload(S.q_base);
+  d_qld = upload(S.q_ld);
+  d_qrp = upload(S.q_rp);
+  d_rowpos = upload(S.rowpos);
+  CK(cudaMalloc(&d_info, sizeof(int)));
+  d_sb = upload(S.sbcols);
+  d_su = upload(S.supds);
+  d_index = upload(S.index);
+  d_porder = upload(S.porder);
+  int maxw = 1;
+  for (const SolveBcol& b : S.sbcols) maxw = std::max(maxw, b.w);
+  set_solve_maxw(maxw);
+  uploaded = true;
+}
+
+void Engine::ensure_solve_buffers(int nrhs) {
+  if (nrhs <= xw_nrhs) return;
+  if (d_xw) CK(cudaFree(d_xw));
+  if (d_x) CK(cudaFree(d_x));
+  CK(cudaMalloc(&d_xw, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
+  CK(cudaMalloc(&d_x, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
+  CK(cudaMemset(d_xw, 0, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
+  xw_nrhs = nrhs;
+}
+
+// Enqueue one factorization: zero L, scatter A, then every launch of the level schedule.
+// phase: -1 = everything; 0 = assemble + launches with depth < split; 1 = the rest.
+void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
+  const Analysis& S = *A;
+  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
+  if (phase <= 0) {
+    CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
+    CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
+    launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
+  }
+  for (const Launch& L : S.launches) {
+    if (phase == 0 && L.depth >= split_depth) continue;
+    if (phase == 1 && L.depth < split_depth) continue;
+    switch (L.kind) {
+      case L_POTRF: launch_potrf(d_potrf + L.begin, L.count, arena, d_info, st); break;
+      case L_TRSM: launch_trsm(d_trsm + L.begin, L.count, arena, st); break;
+      case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
+      case L_TILE_L: launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st); break;
+    }
+  }
+}
+
+void Engine::factor(const double* dval) {
+  upload_tables();
+  if (A->n == 0) return;
+  // The launch sequence is value independent: capture it once, replay it afterwards.
+  if (use_graph && (!factor_graph || graph_val != dval || graph_stream != stream)) {
+    if (factor_graph) {
+      CK(cudaGraphExecDestroy(factor_graph));
+      factor_graph = nullptr;
+    }
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_factor(dval, stream, -1);
+    CK(cudaStreamEndCapture(stream, &g));
+    CK(cudaGraphInstantiate(&factor_graph, g, 0));
+    CK(cudaGraphDestroy(g));
+    graph_val = dval;
+    graph_stream = stream;
+  }
+  if (use_graph)
+    CK(cudaGraphLaunch(factor_graph, stream));
+  else
+    enqueue_factor(dval, stream, -1);
+  factored = true;
+}
+
+void Engine::factor_host(const double* val) {
+  upload_tables();
+  if (A->n == 0) return;
+  CK(cudaMemcpyAsync(d_val, val, A->nnz * sizeof(double), cudaMemcpyHostToDevice, stream));
+  factor(d_val);
+}
+
+void Engine::enqueue_solve(double* dx, int ldx, int nrhs, int job, cudaStream_t st) {
+  const Analysis& S = *A;
+  if (job == 0 || job == 1) {
+    launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
+    for (int d = 0; d < S.ndepth; ++d) {
+      const SolveLaunch& L = S.slaunch[d];
+      launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
+      launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
+    }
+  }
+  if (job == 0 || job == 2) {
+    for (int d = S.ndepth - 1; d >= 0; --d) {
+      const SolveLaunch& L = S.slaunch[d];
+      launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
+      launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
+    }
+    launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
+  }
+}
+
+void Engine::solve(double* dx, int ldx, int nrhs, int job) {
+  upload_tables();
+  if (A->n == 0 || nrhs <= 0) return;
+  ensure_solve_buffers(nrhs);
+  SolveGraphKey key{dx, ldx, nrhs, job, stream, d_xw};
+  if (use_graph) {
+    cudaGraphExec_t ex = nullptr;
+    for (auto& e : solve_graphs)
+      if (e.first == key) ex = e.second;
+    if (!ex) {
+      cudaGraph_t g;
+      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      enqueue_solve(dx, ldx, nrhs, job, stream);
+      CK(cudaStreamEndCapture(stream, &g));
+      CK(cudaGraphInstantiate(&ex, g, 0));
+      CK(cudaGraphDestroy(g));
+      if (solve_graphs.size() >= 8) {
+        CK(cudaGraphExecDestroy(solve_graphs.front().second));
+        solve_graphs.erase(solve_graphs.begin());
+      }
+      solve_graphs.push_back({key, ex});
+    }
+    CK(cudaGraphLaunch(ex, stream));
+  } else {
+    enqueue_solve(dx, ldx, nrhs, job, stream);
+  }
+}
+
+void Engine::solve_host(double* x, int nrhs, int job) {
+  upload_tables();
+  if (A->n == 0 || nrhs <= 0) return;
+  ensure_solve_buffers(nrhs);
+  size_t bytes = (size_t)A->n * nrhs * sizeof(double);
+  // job 2 continues from the device-resident forward result; x is only an output then
+  if (job != 2) CK(cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, stream));
+  solve(d_x, A->n, nrhs, job);
+  if (job != 1) CK(cudaMemcpyAsync(x, d_x, bytes, cudaMemcpyDeviceToHost, stream));
+}
+
+void Engine::sync() {
+  if (stream) CK(cudaStreamSynchronize(stream));
+}
+
+int Engine::pivot_flag() {
+  if (!uploaded || !factored) return 0;
+  int v = 0;
+  sync();
+  CK(cudaMemcpy(&v, d_info, sizeof(int), cudaMemcpyDeviceToHost));
+  return v >= 0x7f000000 ? 0 : v;
+}
+
+void Engine::get_lcol(int g, double* out) {
+  // block column g (0-based) in the reference layout: rows [c*nb, m), cols [c*nb, c*nb+w), ld = w
+  const Analysis& S = *A;
+  const HNode& nd = S.nodes[S.bcol_node[g]];
+  int r0 = S.bcol_c[g] * S.nb;
+  int w = std::min(S.nb, nd.n - r0), h = nd.m - r0;
+  sync();
+  CK(cudaMemcpy2D(out, (size_t)w * sizeof(double), arena + nd.off + (i64)r0 * nd.ld + r0, (size_t)nd.ld * sizeof(double),
+                  (size_t)w * sizeof(double), h, cudaMemcpyDeviceToHost));
+}
+
+void Engine::get_fwd(int nrhs, double* out) {
+  sync();
+  CK(cudaMemcpy(out, d_xw, (size_t)A->n * nrhs * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+void Engine::release() {
+  if (!uploaded) return;
+  cudaDeviceSynchronize();
+  if (factor_graph) cudaGraphExecDestroy(factor_graph);
+  for (auto& e : solve_graphs) cudaGraphExecDestroy(e.second);
+  solve_graphs.clear();
+  factor_graph = nullptr;
+  cudaFree(arena);
+  cudaFree(d_lmap_dst);
+  cudaFree(d_lmap_src);
+  cudaFree(d_val);
+  cudaFree(d_potrf);
+  cudaFree(d_trsm);
+  cudaFree(d_tile);
+  cudaFree(d_qbase);
+  cudaFree(d_qld);
+  cudaFree(d_qrp);
+  cudaFree(d_rowpos);
+  cudaFree(d_info);
+  cudaFree(d_sb);
+  cudaFree(d_su);
+  cudaFree(d_index);
+  cudaFree(d_porder);
+  if (d_xw) cudaFree(d_xw);
+  if (d_x) cudaFree(d_x);
+  if (own_stream) cudaStreamDestroy(own);
+  uploaded = false;
+}
+
+}  // namespace spllt

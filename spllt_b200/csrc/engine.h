@@ -1,0 +1,79 @@
+// Engine: device-side state of one analysed matrix (see engine.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "kernels.cuh"
+#include "model.h"
+
+namespace spllt {
+
+void require_gpu();  // aborts with a clear message when no CUDA device exists (no CPU fallback)
+
+struct SolveGraphKey {
+  double* x;
+  int ldx, nrhs, job;
+  cudaStream_t st;
+  double* xw;
+  bool operator==(const SolveGraphKey& o) const {
+    return x == o.x && ldx == o.ldx && nrhs == o.nrhs && job == o.job && st == o.st && xw == o.xw;
+  }
+};
+
+struct Engine {
+  std::shared_ptr<Analysis> A;
+  int device = 0;
+  bool uploaded = false, factored = false, use_graph = true;
+  cudaStream_t stream = nullptr, own = nullptr;
+  bool own_stream = false;
+  int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
+
+  double* arena = nullptr;
+  i64* d_lmap_dst = nullptr;
+  i64* d_lmap_src = nullptr;
+  double* d_val = nullptr;
+  PanelTask* d_potrf = nullptr;
+  TrsmTask* d_trsm = nullptr;
+  TileTask* d_tile = nullptr;
+  i64* d_qbase = nullptr;
+  int* d_qld = nullptr;
+  i64* d_qrp = nullptr;
+  int* d_rowpos = nullptr;
+  int* d_info = nullptr;
+  SolveBcol* d_sb = nullptr;
+  SolveUpd* d_su = nullptr;
+  int* d_index = nullptr;
+  int* d_porder = nullptr;
+  double* d_xw = nullptr;  // pivot-order work vector, n x nrhs row-major (persists between job 1 and job 2)
+  double* d_x = nullptr;   // staging copy of the caller's host x
+  int xw_nrhs = 0;
+
+  cudaGraphExec_t factor_graph = nullptr;
+  const double* graph_val = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  std::vector<std::pair<SolveGraphKey, cudaGraphExec_t>> solve_graphs;
+
+  // host mirrors requested through spllt_set_mem_solve
+  double* host_y = nullptr;
+  int prep_nb = 0, prep_nrhs = 0;
+
+  void upload_tables();
+  void ensure_solve_buffers(int nrhs);
+  void enqueue_factor(const double* dval, cudaStream_t st, int phase);
+  void factor(const double* dval);
+  void factor_host(const double* val);
+  void enqueue_solve(double* dx, int ldx, int nrhs, int job, cudaStream_t st);
+  void solve(double* dx, int ldx, int nrhs, int job);
+  void solve_host(double* x, int nrhs, int job);
+  void sync();
+  int pivot_flag();
+  void get_lcol(int g, double* out);
+  void get_fwd(int nrhs, double* out);
+  void release();
+  ~Engine() { release(); }
+};
+
+}  // namespace spllt

@@ -1,0 +1,595 @@
+// sm_100a kernels of the SpLLT numerical phase.
+//
+//   k_assemble   a10  spllt_init_node          src/spllt_kernels_mod.F90:2301-2364
+//   k_potrf      a1   spllt_factor_diag_block  :1168-1189   (inner panel diagonal block)
+//   k_trsm       a1/a2 spllt_solve_block       :1217-1229   (rows * L_pp^-T)
+//   k_tile       a3   spllt_update_block       :1261-1292   (intra-node, src < 0)
+//                a4-a7 spllt_update_between + expand_buffer / update_direct
+//                     :2108-2237, :2010-2053, :14-93        (inter-node, fused scatter)
+//   k_fwd_* / k_bwd_*  a13-a15 slv_solve / slv_fwd_update / slv_bwd_update
+//                     src/spllt_solve_kernels_mod.F90:11-210
+//
+// FP64 tensor path: tcgen05 has no f64 kind, so the dense contractions run on
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) fed from multi-stage shared-memory tiles.
+#include <cstdio>
+
+#include "kernels.cuh"
+
+namespace spllt {
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* s, const void* g, int bytes) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* s, const void* g, int bytes) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------------------ assemble
+__global__ void k_assemble(double* __restrict__ arena, const i64* __restrict__ dst, const i64* __restrict__ src,
+                           const double* __restrict__ val, i64 cnt) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (; i < cnt; i += stride) arena[dst[i]] = val[src[i]];
+}
+
+// ------------------------------------------------------------------------------ potrf
+constexpr int PLD = IB + 1;
+__global__ void __launch_bounds__(256) k_potrf(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
+                                               int* __restrict__ info) {
+  __shared__ double a[IB * PLD];
+  const PanelTask t = tasks[blockIdx.x];
+  const int pw = t.pw, tid = threadIdx.x;
+  double* g = arena + t.d_off;
+  for (int idx = tid; idx < pw * pw; idx += 256) {
+    int r = idx / pw, c = idx - r * pw;
+    a[r * PLD + c] = (c <= r) ? g[(i64)r * t.ld + c] : 0.0;
+  }
+  for (int k = 0; k < pw; ++k) {
+    __syncthreads();
+    double akk = a[k * PLD + k];
+    if (!(akk > 0.0) && tid == 0) atomicMin(info, t.col0 + k + 1);
+    double d = sqrt(akk);
+    __syncthreads();
+    if (tid == 0) a[k * PLD + k] = d;
+    int i = k + 1 + tid;
+    if (i < pw) a[i * PLD + k] /= d;
+    __syncthreads();
+    int nt = pw - k - 1;
+    for (int idx = tid; idx < nt * nt; idx += 256) {
+      int ii = idx / nt, jj = idx - ii * nt;
+      if (jj <= ii) a[(k + 1 + ii) * PLD + k + 1 + jj] -= a[(k + 1 + ii) * PLD + k] * a[(k + 1 + jj) * PLD + k];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < pw * pw; idx += 256) {
+    int r = idx / pw, c = idx - r * pw;
+    if (c <= r) g[(i64)r * t.ld + c] = a[r * PLD + c];
+  }
+}
+
+// ------------------------------------------------------------------------------ trsm
+// Each thread owns one row and runs the forward substitution in registers; L_pp is read
+// from shared memory as a broadcast.
+__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__ tasks, double* __restrict__ arena) {
+  extern __shared__ double sm[];
+  double* Ld = sm;               // [IB][PLD]
+  double* X = sm + IB * PLD;     // [TRSM_ROWS][PLD]
+  const TrsmTask t = tasks[blockIdx.x];
+  const int pw = t.pw, tid = threadIdx.x;
+  const double* gd = arena + t.d_off;
+  double* gr = arena + t.r_off;
+  for (int idx = tid; idx < pw * pw; idx += TRSM_ROWS) {
+    int r = idx / pw, c = idx - r * pw;
+    Ld[r * PLD + c] = gd[(i64)r * t.ld + c];
+  }
+  for (int idx = tid; idx < t.nrows * pw; idx += TRSM_ROWS) {
+    int r = idx / pw, c = idx - r * pw;
+    X[r * PLD + c] = gr[(i64)r * t.ld + c];
+  }
+  __syncthreads();
+  if (tid < t.nrows) {
+    double x[IB];
+#pragma unroll
+    for (int c = 0; c < IB; ++c) x[c] = (c < pw) ? X[tid * PLD + c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < IB; ++c) {
+      if (c < pw) {
+        double s = x[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) s -= x[k] * Ld[c * PLD + k];
+        x[c] = s / Ld[c * PLD + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < IB; ++c)
+      if (c < pw) X[tid * PLD + c] = x[c];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < t.nrows * pw; idx += TRSM_ROWS) {
+    int r = idx / pw, c = idx - r * pw;
+    gr[(i64)r * t.ld + c] = X[r * PLD + c];
+  }
+}
+
+// ------------------------------------------------------------------------------ tile update
+constexpr int KC = 16;          // K chunk per pipeline stage
+constexpr int SLD = KC + 4;     // padded shared row: (r*SLD + k) mod 16 distinct for r<4, k<4
+constexpr int NSTAGE = 3;
+
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+    k_tile(const TileTask* __restrict__ tasks, double* __restrict__ arena, DevMaps mp) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  constexpr int FM = WM / 8, FN = WN / 8;
+  extern __shared__ __align__(16) double sm[];
+  double* As = sm;                          // [NSTAGE][BM][SLD]
+  double* Bs = sm + NSTAGE * BM * SLD;      // [NSTAGE][BN][SLD]
+  const TileTask t = tasks[blockIdx.x];
+  const double* base = arena + t.off;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
+  const bool al = ((t.k0 & 1) == 0);
+  const int nch = (t.kk + KC - 1) / KC;
+
+  auto load_stage = [&](int ch, int st) {
+    const int kb = ch * KC;
+    for (int c = tid; c < (BM + BN) * (KC / 2); c += NT) {
+      int r = c / (KC / 2), q = (c % (KC / 2)) * 2;
+      double* s;
+      int row;
+      if (r < BM) {
+        s = As + (st * BM + r) * SLD + q;
+        row = t.i0 + min(r, t.mt - 1);
+      } else {
+        s = Bs + (st * BN + (r - BM)) * SLD + q;
+        row = t.j0 + min(r - BM, t.nt - 1);
+      }
+      int k = kb + q;
+      int valid = min(max(t.kk - k, 0), 2);
+      const double* g = base + (i64)row * t.ld + t.k0 + k;
+      if (al) {
+        cp_async16(s, valid ? g : base, valid * 8);
+      } else {
+        cp_async8(s, valid > 0 ? g : base, valid > 0 ? 8 : 0);
+        cp_async8(s + 1, valid > 1 ? g + 1 : base, valid > 1 ? 8 : 0);
+      }
+    }
+  };
+
+  double acc[FM][FN][2];
+#pragma unroll
+  for (int i = 0; i < FM; ++i)
+#pragma unroll
+    for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // warps whose sub-tile lies strictly above the diagonal have nothing to contribute
+  const bool active = (t.i0 + wm0 + WM - 1 >= t.j0 + wn0) && (wm0 < t.mt) && (wn0 < t.nt);
+
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < nch) load_stage(s, s);
+    cp_commit();
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    cp_wait<NSTAGE - 2>();
+    __syncthreads();
+    int nx = ch + NSTAGE - 1;
+    if (nx < nch) load_stage(nx, nx % NSTAGE);
+    cp_commit();
+    if (active) {
+      const double* a = As + ((ch % NSTAGE) * BM + wm0 + (lane >> 2)) * SLD + (lane & 3);
+      const double* b = Bs + ((ch % NSTAGE) * BN + wn0 + (lane >> 2)) * SLD + (lane & 3);
+#pragma unroll
+      for (int k4 = 0; k4 < KC; k4 += 4) {
+        double af[FM], bf[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) af[i] = a[i * 8 * SLD + k4];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) bf[j] = b[j * 8 * SLD + k4];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+  }
+  cp_wait<0>();
+  if (!active) return;
+
+  const bool scatter = t.src >= 0;
+#pragma unroll
+  for (int i = 0; i < FM; ++i) {
+    int ii = wm0 + i * 8 + (lane >> 2);
+    if (ii >= t.mt) continue;
+    int gi = t.i0 + ii;
+#pragma unroll
+    for (int j = 0; j < FN; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int jj = wn0 + j * 8 + 2 * (lane & 3) + e;
+        int gj = t.j0 + jj;
+        if (jj >= t.nt || gi < gj) continue;
+        double v = acc[i][j][e];
+        if (!scatter) {
+          double* c = arena + t.off + (i64)gi * t.ld + gj;
+          *c -= v;
+        } else {
+          i64 q = t.qoff + gj;
+          double* c = arena + mp.q_base[q] + (i64)mp.rowpos[mp.q_rp[q] + gi] * mp.q_ld[q];
+          atomicAdd(c, -v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ peak probes
+__global__ void __launch_bounds__(256) k_dmma_peak(int iters, double* sink) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double* sink) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------ solve
+// Work vector xw is in pivot order, row-major n x nrhs (the nrhs values of one row are
+// contiguous), so gathers through node%index move whole rows.
+__global__ void k_permute_in(const double* __restrict__ x, int ldx, const int* __restrict__ porder,
+                             double* __restrict__ xw, int n, int nrhs) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (i64)n * nrhs) return;
+  int p = (int)(i / nrhs), r = (int)(i % nrhs);
+  xw[i] = x[porder[p] + (i64)r * ldx];
+}
+__global__ void k_permute_out(double* __restrict__ x, int ldx, const int* __restrict__ porder,
+                              const double* __restrict__ xw, int n, int nrhs) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (i64)n * nrhs) return;
+  int p = (int)(i / nrhs), r = (int)(i % nrhs);
+  x[porder[p] + (i64)r * ldx] = xw[i];
+}
+
+constexpr int SB = 32;        // sub-block of the in-CTA triangular solves
+constexpr int SBL = SB + 1;
+
+// Forward: solve L_cc x = b for one block column (w x w lower triangle, row-major).
+template <int RC>
+__global__ void __launch_bounds__(256) k_fwd_diag(const SolveBcol* __restrict__ bcs, const double* __restrict__ arena,
+                                                  double* __restrict__ xw, int nrhs) {
+  extern __shared__ double sm[];
+  const SolveBcol b = bcs[blockIdx.x];
+  const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
+  double* xs = sm;                 // [RC][wp]
+  double* Ls = sm + RC * wp;       // [SB][SBL]
+  const double* L = arena + b.off + (i64)b.r0 * b.ld + b.r0;
+  double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
+  for (int idx = tid; idx < w * nr; idx += 256) {
+    int k = idx / nr, q = idx - k * nr;
+    xs[q * wp + k] = xg[(i64)k * nrhs + q];
+  }
+  for (int jb = 0; jb < w; jb += SB) {
+    const int bs = min(SB, w - jb);
+    __syncthreads();
+    for (int idx = tid; idx < bs * SB; idx += 256) {
+      int i = idx >> 5, k = idx & 31;
+      Ls[i * SBL + k] = (k <= i) ? L[(i64)(jb + i) * b.ld + jb + k] : 0.0;
+    }
+    __syncthreads();
+    for (int q = warp; q < nr; q += 8) {
+      double xi = (lane < bs) ? xs[q * wp + jb + lane] : 0.0;
+      double rinv = (lane < bs) ? 1.0 / Ls[lane * SBL + lane] : 0.0;
+      for (int k = 0; k < bs; ++k) {
+        double xk = __shfl_sync(FULL, xi * rinv, k);
+        if (lane == k) xi = xk;
+        if (lane > k && lane < bs) xi -= Ls[lane * SBL + k] * xk;
+      }
+      if (lane < bs) xs[q * wp + jb + lane] = xi;
+    }
+    __syncthreads();
+    for (int i = jb + bs + tid; i < w; i += 256) {
+      const double* lr = L + (i64)i * b.ld + jb;
+      double s[RC];
+#pragma unroll
+      for (int q = 0; q < RC; ++q) s[q] = 0.0;
+      for (int k = 0; k < bs; ++k) {
+        double l = lr[k];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) s[q] += l * xs[q * wp + jb + k];
+      }
+#pragma unroll
+      for (int q = 0; q < RC; ++q)
+        if (q < nr) xs[q * wp + i] -= s[q];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < w * nr; idx += 256) {
+    int k = idx / nr, q = idx - k * nr;
+    xg[(i64)k * nrhs + q] = xs[q * wp + k];
+  }
+}
+
+// Forward update: xw[index[r]] -= L[r, bcol] * x_bcol for a chunk of rows below the block column.
+template <int RC>
+__global__ void __launch_bounds__(256) k_fwd_upd(const SolveUpd* __restrict__ ups, const SolveBcol* __restrict__ bcs,
+                                                 const double* __restrict__ arena, const int* __restrict__ index,
+                                                 double* __restrict__ xw, int nrhs) {
+  extern __shared__ double sm[];
+  const SolveUpd u = ups[blockIdx.x];
+  const SolveBcol b = bcs[u.bc];
+  const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
+  double* xs = sm;  // [RC][wp]
+  const double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
+  for (int idx = tid; idx < w * RC; idx += 256) {
+    int k = idx / RC, q = idx - k * RC;
+    xs[q * wp + k] = (q < nr) ? xg[(i64)k * nrhs + q] : 0.0;
+  }
+  __syncthreads();
+  int g = 32;  // lanes cooperating on one row
+  while (g > 4 && (g >> 1) >= w) g >>= 1;
+  const int rpw = 32 / g, sub = lane / g, lg = lane % g;
+  const double* L = arena + b.off + (i64)u.r * b.ld + b.r0;
+  const int* idx = index + b.idx_off + u.r;
+  for (int base = warp * rpw; base < u.nrows; base += 8 * rpw) {
+    int row = base + sub;
+    bool ok = row < u.nrows;
+    double s[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) s[q] = 0.0;
+    if (ok) {
+      const double* lr = L + (i64)row * b.ld;
+      for (int k = lg; k < w; k += g) {
+        double l = lr[k];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) s[q] += l * xs[q * wp + k];
+      }
+    }
+    for (int o = g >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < RC; ++q) s[q] += __shfl_xor_sync(FULL, s[q], o);
+    }
+    if (ok && lg == 0) {
+      double* dst = xw + (i64)idx[row] * nrhs + rc0;
+#pragma unroll
+      for (int q = 0; q < RC; ++q)
+        if (q < nr) atomicAdd(dst + q, -s[q]);
+    }
+  }
+}
+
+// Backward update: x_bcol -= L[rows, bcol]^T * xw[index[rows]].
+template <int RC>
+__global__ void __launch_bounds__(256) k_bwd_upd(const SolveUpd* __restrict__ ups, const SolveBcol* __restrict__ bcs,
+                                                 const double* __restrict__ arena, const int* __restrict__ index,
+                                                 double* __restrict__ xw, int nrhs) {
+  __shared__ double ys[RC][SOLVE_ROWS];
+  const SolveUpd u = ups[blockIdx.x];
+  const SolveBcol b = bcs[u.bc];
+  const int w = b.w, tid = threadIdx.x;
+  const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
+  const int* idx = index + b.idx_off + u.r;
+  for (int i = tid; i < u.nrows * RC; i += 256) {
+    int row = i / RC, q = i - row * RC;
+    ys[q][row] = (q < nr) ? xw[(i64)idx[row] * nrhs + rc0 + q] : 0.0;
+  }
+  __syncthreads();
+  int tw = 256;  // threads across columns
+  while (tw > 4 && (tw >> 1) >= w) tw >>= 1;
+  const int tx = tid % tw, ty = tid / tw, ny = 256 / tw;
+  const double* L = arena + b.off + (i64)u.r * b.ld + b.r0;
+  double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
+  for (int k = tx; k < w; k += tw) {
+    double s[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) s[q] = 0.0;
+    for (int row = ty; row < u.nrows; row += ny) {
+      double l = L[(i64)row * b.ld + k];
+#pragma unroll
+      for (int q = 0; q < RC; ++q) s[q] += l * ys[q][row];
+    }
+#pragma unroll
+    for (int q = 0; q < RC; ++q)
+      if (q < nr) atomicAdd(xg + (i64)k * nrhs + q, -s[q]);
+  }
+}
+
+// Backward: solve L_cc^T x = b.
+template <int RC>
+__global__ void __launch_bounds__(256) k_bwd_diag(const SolveBcol* __restrict__ bcs, const double* __restrict__ arena,
+                                                  double* __restrict__ xw, int nrhs) {
+  extern __shared__ double sm[];
+  const SolveBcol b = bcs[blockIdx.x];
+  const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
+  double* xs = sm;
+  double* Ls = sm + RC * wp;
+  const double* L = arena + b.off + (i64)b.r0 * b.ld + b.r0;
+  double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
+  for (int idx = tid; idx < w * nr; idx += 256) {
+    int k = idx / nr, q = idx - k * nr;
+    xs[q * wp + k] = xg[(i64)k * nrhs + q];
+  }
+  const int nblk = (w + SB - 1) / SB;
+  for (int ib = nblk - 1; ib >= 0; --ib) {
+    const int jb = ib * SB, bs = min(SB, w - jb);
+    __syncthreads();
+    for (int idx = tid; idx < bs * SB; idx += 256) {
+      int i = idx >> 5, k = idx & 31;
+      Ls[i * SBL + k] = (k <= i) ? L[(i64)(jb + i) * b.ld + jb + k] : 0.0;
+    }
+    __syncthreads();
+    for (int q = warp; q < nr; q += 8) {
+      double xi = (lane < bs) ? xs[q * wp + jb + lane] : 0.0;
+      double rinv = (lane < bs) ? 1.0 / Ls[lane * SBL + lane] : 0.0;
+      for (int k = bs - 1; k >= 0; --k) {
+        double xk = __shfl_sync(FULL, xi * rinv, k);
+        if (lane == k) xi = xk;
+        if (lane < k) xi -= Ls[k * SBL + lane] * xk;
+      }
+      if (lane < bs) xs[q * wp + jb + lane] = xi;
+    }
+    __syncthreads();
+    for (int i = tid; i < jb; i += 256) {
+      double s[RC];
+#pragma unroll
+      for (int q = 0; q < RC; ++q) s[q] = 0.0;
+      for (int k = 0; k < bs; ++k) {
+        double l = L[(i64)(jb + k) * b.ld + i];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) s[q] += l * xs[q * wp + jb + k];
+      }
+#pragma unroll
+      for (int q = 0; q < RC; ++q)
+        if (q < nr) xs[q * wp + i] -= s[q];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < w * nr; idx += 256) {
+    int k = idx / nr, q = idx - k * nr;
+    xg[(i64)k * nrhs + q] = xs[q * wp + k];
+  }
+}
+
+// ------------------------------------------------------------------------------ launchers
+constexpr int SMEM_TRSM = (IB * PLD + TRSM_ROWS * PLD) * 8;
+constexpr int SMEM_TILE_S = NSTAGE * (64 + 64) * SLD * 8;
+constexpr int SMEM_TILE_L = NSTAGE * (128 + 128) * SLD * 8;
+constexpr int SMEM_SOLVE_MAX = 200 * 1024;
+
+#define CK(x)                                                                             \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) {                                                              \
+      fprintf(stderr, "spllt_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      abort();                                                                            \
+    }                                                                                     \
+  } while (0)
+
+void kernels_init() {
+  CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TRSM));
+  CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
+  CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
+  CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+  CK(cudaFuncSetAttribute(k_fwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+  CK(cudaFuncSetAttribute(k_bwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+  CK(cudaFuncSetAttribute(k_bwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+  CK(cudaFuncSetAttribute(k_fwd_upd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+  CK(cudaFuncSetAttribute(k_fwd_upd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+}
+
+void launch_assemble(double* arena, const i64* dst, const i64* src, const double* val, i64 cnt, cudaStream_t st) {
+  if (cnt <= 0) return;
+  int blocks = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
+  k_assemble<<<blocks, 256, 0, st>>>(arena, dst, src, val, cnt);
+}
+void launch_potrf(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st) {
+  if (count > 0) k_potrf<<<(unsigned)count, 256, 0, st>>>(tasks, arena, info);
+}
+void launch_trsm(const TrsmTask* tasks, i64 count, double* arena, cudaStream_t st) {
+  if (count > 0) k_trsm<<<(unsigned)count, TRSM_ROWS, SMEM_TRSM, st>>>(tasks, arena);
+}
+void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
+  if (count <= 0) return;
+  if (large)
+    k_tile<128, 128, 64, 32><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
+  else
+    k_tile<64, 64, 32, 32><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
+}
+
+void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st) {
+  i64 tot = (i64)n * nrhs;
+  if (tot > 0) k_permute_in<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, ldx, porder, xw, n, nrhs);
+}
+void launch_permute_out(double* x, int ldx, const int* porder, const double* xw, int n, int nrhs, cudaStream_t st) {
+  i64 tot = (i64)n * nrhs;
+  if (tot > 0) k_permute_out<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, ldx, porder, xw, n, nrhs);
+}
+
+static inline int solve_smem(int maxw, int rc, bool tri) { return (rc * (maxw + 1) + (tri ? SB * SBL : 0)) * 8; }
+static int g_maxw = 1024;
+void set_solve_maxw(int w) { g_maxw = w; }
+
+void launch_fwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st) {
+  if (count <= 0) return;
+  if (nrhs == 1)
+    k_fwd_diag<1><<<dim3((unsigned)count, 1), 256, solve_smem(g_maxw, 1, true), st>>>(bc, arena, xw, nrhs);
+  else
+    k_fwd_diag<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, solve_smem(g_maxw, 8, true), st>>>(bc, arena, xw, nrhs);
+}
+void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st) {
+  if (count <= 0) return;
+  if (nrhs == 1)
+    k_bwd_diag<1><<<dim3((unsigned)count, 1), 256, solve_smem(g_maxw, 1, true), st>>>(bc, arena, xw, nrhs);
+  else
+    k_bwd_diag<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, solve_smem(g_maxw, 8, true), st>>>(bc, arena, xw, nrhs);
+}
+void launch_fwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
+                    double* xw, int nrhs, cudaStream_t st) {
+  if (count <= 0) return;
+  if (nrhs == 1)
+    k_fwd_upd<1><<<dim3((unsigned)count, 1), 256, solve_smem(g_maxw, 1, false), st>>>(up, bc, arena, index, xw, nrhs);
+  else
+    k_fwd_upd<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, solve_smem(g_maxw, 8, false), st>>>(up, bc, arena, index,
+                                                                                                 xw, nrhs);
+}
+void launch_bwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
+                    double* xw, int nrhs, cudaStream_t st) {
+  if (count <= 0) return;
+  if (nrhs == 1)
+    k_bwd_upd<1><<<dim3((unsigned)count, 1), 256, 0, st>>>(up, bc, arena, index, xw, nrhs);
+  else
+    k_bwd_upd<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, 0, st>>>(up, bc, arena, index, xw, nrhs);
+}
+
+static double* g_sink = nullptr;
+double launch_dmma_peak(int iters, cudaStream_t st) {
+  if (!g_sink) CK(cudaMalloc(&g_sink, 64));
+  int blocks = 148 * 8;
+  k_dmma_peak<<<blocks, 256, 0, st>>>(iters, g_sink);
+  return (double)blocks * 8 * (double)iters * 16 * 512.0;
+}
+double launch_dfma_peak(int iters, cudaStream_t st) {
+  if (!g_sink) CK(cudaMalloc(&g_sink, 64));
+  int blocks = 148 * 8;
+  k_dfma_peak<<<blocks, 256, 0, st>>>(iters, g_sink);
+  return (double)blocks * 256 * (double)iters * 16 * 2.0;
+}
+
+}  // namespace spllt

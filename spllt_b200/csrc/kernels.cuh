@@ -1,0 +1,38 @@
+// Launch wrappers of the sm_100a kernels (kernels.cu).  All pointers are device pointers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "model.h"
+
+namespace spllt {
+
+struct DevMaps {          // inter-node update maps (device copies of Analysis::q_*)
+  const i64* q_base;
+  const int* q_ld;
+  const i64* q_rp;
+  const int* rowpos;
+};
+
+void kernels_init();      // opt-in shared memory sizes; call once per process
+void set_solve_maxw(int w);  // widest block column the solve kernels will see (shared memory size)
+void launch_assemble(double* arena, const i64* dst, const i64* src, const double* val, i64 cnt, cudaStream_t st);
+void launch_potrf(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st);
+void launch_trsm(const TrsmTask* tasks, i64 count, double* arena, cudaStream_t st);
+void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st);
+
+// solve
+void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st);
+void launch_permute_out(double* x, int ldx, const int* porder, const double* xw, int n, int nrhs, cudaStream_t st);
+void launch_fwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st);
+void launch_fwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
+                    double* xw, int nrhs, cudaStream_t st);
+void launch_bwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
+                    double* xw, int nrhs, cudaStream_t st);
+void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st);
+
+// FP64 tensor-pipe peak probe: every warp of every SM runs register-resident DMMA.
+// Returns flops issued; time it with events.
+double launch_dmma_peak(int iters, cudaStream_t st);
+double launch_dfma_peak(int iters, cudaStream_t st);
+
+}  // namespace spllt

@@ -1,0 +1,163 @@
+// Flat (SoA) data model of the B200 build: what spllt_data_mod's derived types
+// (src/spllt_data_mod.F90:83-388: spllt_block, spllt_node, lfactor, lmap_type,
+// spllt_sblock_t, spllt_akeep, spllt_fkeep) become when node / block storage moves to HBM.
+//
+// Host side keeps the symbolic content (value independent, produced by spllt_analyse);
+// the device side holds one HBM arena for all supernodes plus the work lists that
+// replace the OpenMP / StarPU task DAG (src/spllt_factorization_task_mod.F90).
+//
+// HBM layout: every supernode is ONE row-major m x ld matrix (ld = n rounded up to 4,
+// padding columns stay zero).  Block column c of the reference (lfact(bcol)%lcol, row-major
+// tiles with ld = blkn, src/spllt_analyse_mod.F90:1160-1165) is the sub-matrix
+// rows [c*nb, m) x cols [c*nb, c*nb+blkn) of that matrix, so the reference layout is
+// recovered by a strided copy (capi: spllt_b200_get_factor).
+//
+// Internal indices are 0-based; getters convert to the reference's 1-based tables so they
+// can be compared bit-for-bit with the oracle.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "symbolic.h"
+
+namespace spllt {
+
+typedef int64_t i64;
+
+constexpr int IB = 64;      // inner panel width of the block-column factorization
+constexpr int LDPAD = 4;    // node leading dimension is a multiple of 4 doubles (32 B)
+constexpr int TRSM_ROWS = 128;  // rows per CTA of the panel solve
+constexpr int SOLVE_ROWS = 256; // rows per CTA of the solve update kernels
+
+// ------------------------------------------------------------------ host symbolic tables
+struct HNode {
+  int sa, en;        // first / last column (0-based, pivot order)
+  int m, n;          // rows, columns
+  i64 idx_off;       // node index list = index[idx_off .. idx_off+m)
+  int parent;        // 0-based, -1 for roots (the reference's virtual root nnodes+1)
+  int nchild;
+  int least_desc;    // first node of the subtree (postorder => subtree = [least_desc, self])
+  int nc, nr;        // block columns, block rows
+  int bcol0;         // first global block column (0-based)
+  i64 blk0;          // first tile id (0-based)
+  int depth0;        // schedule depth of block column 0 (block column c runs at depth0 + c)
+  int small;         // pruning mark (reference semantics: 0, 1, -root(1-based))
+  int owner;         // GPU rank that owns the node (multi-GPU); -1 = shared top of the tree
+  int ld;            // leading dimension in the arena
+  i64 off;           // arena offset (doubles)
+  i64 row_base;      // first below-diagonal row of this node in the q_* update maps
+};
+
+// ------------------------------------------------------------------ device work lists
+// Factorization of one inner panel's diagonal block (a1, src/spllt_kernels_mod.F90:1168).
+struct PanelTask {
+  i64 d_off;         // arena offset of the pw x pw diagonal block
+  int ld, pw;
+  int col0;          // global pivot column of the panel's first column (error report)
+  int pad;
+};
+// Panel solve rows <- rows * L_pp^-T  (a1 trapezoid part + a2, :1179-1186, :1217-1229).
+struct TrsmTask {
+  i64 d_off;         // diagonal block
+  i64 r_off;         // first row of this chunk
+  int ld, pw, nrows, pad;
+};
+// One dense tile update (a3 intra-node, a4 inter-node):
+//   C[i, j] -= sum_{k in [k0, k0+kk)} L[i, k] * L[j, k],  i in [i0,i0+mt), j in [j0,j0+nt), i >= j
+// rows/cols are row numbers of the SOURCE node's matrix.  src < 0: C is the same node
+// (column j of the node == row j).  src >= 0: scatter through the q_* maps into ancestors.
+struct TileTask {
+  i64 off;           // arena offset of the source node
+  int ld;
+  int i0, j0, k0;
+  int mt, nt, kk;
+  int src;
+  i64 qoff;          // row_base - n of the source (index of row r in the maps = qoff + r)
+};
+
+enum LaunchKind { L_POTRF = 0, L_TRSM = 1, L_TILE_S = 2, L_TILE_L = 3 };
+struct Launch {
+  int kind;
+  int depth;
+  i64 begin;         // first task in the list of this kind
+  i64 count;         // tasks (= CTAs)
+};
+
+// ------------------------------------------------------------------ solve work lists
+// One block column in the supernodal triangular solves (a13/a14).
+struct SolveBcol {
+  i64 off;           // arena offset of the node
+  i64 idx_off;       // node index list
+  int ld, m;
+  int r0, w;         // first row/col of the block column inside the node, width
+  int sa;            // first pivot column of the node
+  int pad;
+};
+struct SolveUpd {    // rows [r, r+nrows) of block column `bc` (index into the SolveBcol list)
+  int bc, r, nrows, pad;
+};
+struct SolveLaunch {
+  i64 diag_begin, diag_count;   // SolveBcol range
+  i64 upd_begin, upd_count;     // SolveUpd range
+};
+
+// ------------------------------------------------------------------ reference-format tables
+struct RefBlock {    // spllt_block, 1-based (src/spllt_data_mod.F90:123-172)
+  i64 id;
+  int blkm, blkn;
+  i64 sa, dblk, last_blk;
+  int node, bcol, dep_initial;
+};
+
+struct Analysis {
+  int n = 0, nb = 0, nemin = 32, ncpu = 1, prune = 1, min_width_blas = 8;
+  i64 nnz = 0;               // entries of the user's lower triangle
+  Symbolic sym;
+  std::vector<int> porder;   // porder[p] = variable at pivot position p (0-based both)
+
+  int nnodes = 0, nbcol = 0, ndepth = 0, maxmn = 0;
+  i64 final_blk = 0;
+  std::vector<HNode> nodes;
+  std::vector<int> index;          // concatenated row lists (0-based pivot indices)
+  std::vector<i64> weight;         // [nnodes+1] flops per subtree (+ virtual root)
+  std::vector<int> col2node;       // pivot column -> node
+
+  // A -> L map (spllt_make_map + spllt_lcol_map), grouped by block column
+  std::vector<i64> lmap_ptr;       // [nbcol+1]
+  std::vector<int> lmap_row;       // row inside the NODE (0-based)
+  std::vector<int> lmap_col;       // column inside the NODE (0-based)
+  std::vector<i64> lmap_src;       // 0-based index into the user's val
+  std::vector<int> bcol_node;      // [nbcol] owning node
+  std::vector<int> bcol_c;         // [nbcol] local block-column index
+
+  i64 arena = 0;                   // device arena size (doubles)
+  i64 top_begin = 0;               // arena offset where the upper tree (small == 0) starts
+  i64 num_factor = 0;              // entries of L (trapezoids, reference count)
+  i64 num_flops = 0;               // sum_nodes sum_j (m-n+j)^2  (akeep%weight(nnodes+1))
+
+  // factor schedule
+  std::vector<PanelTask> potrf_tasks;
+  std::vector<TrsmTask> trsm_tasks;
+  std::vector<TileTask> tile_tasks;
+  std::vector<Launch> launches;
+  std::vector<i64> q_base;         // per below-diagonal row: dest address when used as a COLUMN
+  std::vector<int> q_ld;           //   leading dimension of that dest node
+  std::vector<i64> q_rp;           //   rowpos[q_rp[j] + r] = row position of source row r in dest
+  std::vector<int> rowpos;
+  double tile_flops = 0;           // flops issued by the tile kernels (incl. masked halves)
+
+  // solve schedule (forward order; the backward sweep walks it in reverse)
+  std::vector<SolveBcol> sbcols;
+  std::vector<SolveUpd> supds;
+  std::vector<SolveLaunch> slaunch;   // one per depth
+};
+
+// analyse.cpp
+int build_analysis(int n, const int* ptr, const int* row, int nb, int nemin, int ncpu, int prune,
+                   int ordering, const int* user_order, Analysis& A);
+void prune_tree(Analysis& A, int nth, std::vector<int>& small);
+void build_factor_schedule(Analysis& A, int tile_l_min);
+void build_solve_schedule(Analysis& A);
+void ref_blocks(const Analysis& A, std::vector<RefBlock>& out);
+
+}  // namespace spllt
