@@ -72,8 +72,13 @@ int spllt_b200_chkerr(int n, const int *ptr, const int *row, const double *val, 
 long long spllt_b200_factor_launches(void *fkeep);  /* kernels per spllt_factor             */
 long long spllt_b200_solve_launches(void *fkeep, int job);
 double spllt_b200_tile_flops(void *akeep);          /* flops issued by the DMMA tile kernels */
-/* per-kernel-kind launch counts of one factorization: potrf, trsm, tile_s, tile_l */
+/* launch counts of one factorization: panel, tile_s, tile_l, total */
 void spllt_b200_launch_breakdown(void *akeep, long long *out4);
+
+/* diagnostic: one un-graphed factorization timed launch by launch; ms4 = milliseconds spent in
+ * {memset+assemble, panel (potrf+trsm), 64x64 tiles, 128x128 tiles}; csv (may be NULL) receives
+ * one line per launch.  Synchronises. */
+void spllt_b200_profile_factor(void *fkeep, const double *d_val, double *ms4, const char *csv);
 
 /* ---- FP64 peak probes (no FP64 figure in MEASURED_PEAKS.json): enqueue a register-resident
  * DMMA (kind 0) or DFMA (kind 1) loop on every SM; returns the flops it will execute */
@@ -85,6 +90,7 @@ void *spllt_b200_arena_ptr(void *fkeep);            /* device pointer of the HBM
 /* node ownership: rank r factorizes the subtrees given to it by proportional mapping; nodes
  * above the split are "shared" (owner -1) and factorized by every rank after the reduction */
 void spllt_b200_partition(void *akeep, void *fkeep, int rank, int world);
+int spllt_b200_node_owner(void *akeep, int node);  /* node 1-based; -1 = shared top */
 /* [begin, end) offsets (doubles) of the shared top-of-tree region in the arena */
 void spllt_b200_shared_region(void *akeep, long long *begin, long long *end);
 /* phase 0 = assemble + local subtrees, phase 1 = shared top; both asynchronous */

@@ -104,6 +104,8 @@ def load_library(path=None):
         "spllt_b200_solve_launches": (C.c_longlong, [vp, C.c_int]),
         "spllt_b200_tile_flops": (C.c_double, [vp]),
         "spllt_b200_launch_breakdown": (None, [vp, llp]),
+        "spllt_b200_profile_factor": (None, [vp, vp, dp, C.c_char_p]),
+        "spllt_b200_node_owner": (C.c_int, [vp, C.c_int]),
         "spllt_b200_peak_probe": (C.c_double, [C.c_int, C.c_int, vp]),
         "spllt_b200_arena_ptr": (vp, [vp]),
         "spllt_b200_partition": (None, [vp, vp, C.c_int, C.c_int]),
@@ -196,6 +198,12 @@ class SpLLT:
                                    C.byref(self.info))
         return self.worksize
 
+    def prepare_solve_size(self, nrhs, nb=None):
+        ws = C.c_long(0)
+        self.L.spllt_prepare_solve(self.akeep, self.fkeep, self.options.nb if nb is None else nb, nrhs,
+                                   C.byref(ws), C.byref(self.info))
+        return ws.value
+
     def solve(self, x, job=0):
         """x: n or n x nrhs (column-major), overwritten in place; job 0/1/2 as in the reference."""
         assert x.dtype == np.float64 and (x.ndim == 1 or x.flags.f_contiguous)
@@ -235,6 +243,12 @@ class SpLLT:
         self.L.spllt_b200_solve_dev(self.fkeep, nrhs, C.c_void_p(d_x_ptr), self.n if ldx is None else ldx, job,
                                     C.byref(self.info))
         return self.info.flag
+
+    def profile_factor(self, d_val_ptr, csv=None):
+        ms = np.zeros(4)
+        self.L.spllt_b200_profile_factor(self.fkeep, C.c_void_p(d_val_ptr), _dp(ms),
+                                         csv.encode() if csv else None)
+        return dict(zip(("assemble", "panel", "tile_s", "tile_l"), ms.tolist()))
 
     def pivot_flag(self):
         return self.L.spllt_b200_pivot_flag(self.fkeep)

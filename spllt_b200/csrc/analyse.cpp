@@ -355,8 +355,7 @@ static void add_tiles(Analysis& A, std::vector<TileTask>& small, std::vector<Til
 
 void build_factor_schedule(Analysis& A, int tile_l_min) {
   const int nn = A.nnodes, nb = A.nb;
-  A.potrf_tasks.clear();
-  A.trsm_tasks.clear();
+  A.panel_tasks.clear();
   A.tile_tasks.clear();
   A.launches.clear();
   A.tile_flops = 0;
@@ -395,78 +394,109 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     }
   }
 
-  // ---- level sets
-  std::vector<std::vector<int>> at(A.ndepth);  // global block-column ids per depth
-  for (int s = 0; s < nn; ++s)
-    for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
-
+  // ---- level sets, one pass per phase (phase 0: nodes owned by this rank, phase 1: shared top)
   std::vector<TileTask> ts, tl;
-  auto flush_tiles = [&](int depth) {
+  int cur_phase = 0;
+  auto flush_tiles = [&](int depth, int tag) {
     if (!ts.empty()) {
-      A.launches.push_back({L_TILE_S, depth, (i64)A.tile_tasks.size(), (i64)ts.size()});
+      A.launches.push_back({L_TILE_S, depth, (i64)A.tile_tasks.size(), (i64)ts.size(), cur_phase, tag});
       A.tile_tasks.insert(A.tile_tasks.end(), ts.begin(), ts.end());
       ts.clear();
     }
     if (!tl.empty()) {
-      A.launches.push_back({L_TILE_L, depth, (i64)A.tile_tasks.size(), (i64)tl.size()});
+      A.launches.push_back({L_TILE_L, depth, (i64)A.tile_tasks.size(), (i64)tl.size(), cur_phase, tag});
       A.tile_tasks.insert(A.tile_tasks.end(), tl.begin(), tl.end());
       tl.clear();
     }
   };
 
-  for (int d = 0; d < A.ndepth; ++d) {
-    int maxsteps = 0;
-    for (int g : at[d]) {
-      const HNode& nd = A.nodes[A.bcol_node[g]];
-      int w = std::min(nb, nd.n - A.bcol_c[g] * nb);
-      maxsteps = std::max(maxsteps, cdiv(w, IB));
+  for (int phase = 0; phase < 2; ++phase) {
+    cur_phase = phase;
+    std::vector<std::vector<int>> at(A.ndepth);  // global block-column ids per depth
+    for (int s = 0; s < nn; ++s) {
+      int own = A.nodes[s].owner;
+      bool mine = (A.world <= 1) ? (phase == 0) : (phase == 0 ? own == A.rank : own < 0);
+      if (!mine) continue;
+      for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
     }
-    for (int p = 0; p < maxsteps; ++p) {
-      i64 p0 = A.potrf_tasks.size(), t0 = A.trsm_tasks.size();
+    for (int d = 0; d < A.ndepth; ++d) {
+      if (at[d].empty()) continue;
+      int maxsteps = 0;
       for (int g : at[d]) {
         const HNode& nd = A.nodes[A.bcol_node[g]];
-        int r0 = A.bcol_c[g] * nb;
-        int w = std::min(nb, nd.n - r0);
-        if (p * IB >= w) continue;
-        int pw = std::min(IB, w - p * IB);
-        int k0 = r0 + p * IB;
-        PanelTask pt;
-        pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
-        pt.ld = nd.ld;
-        pt.pw = pw;
-        pt.col0 = nd.sa + k0;
-        pt.pad = 0;
-        A.potrf_tasks.push_back(pt);
-        for (int r = k0 + pw; r < nd.m; r += TRSM_ROWS) {
-          TrsmTask tt;
-          tt.d_off = pt.d_off;
-          tt.r_off = nd.off + (i64)r * nd.ld + k0;
-          tt.ld = nd.ld;
-          tt.pw = pw;
-          tt.nrows = std::min(TRSM_ROWS, nd.m - r);
-          tt.pad = 0;
-          A.trsm_tasks.push_back(tt);
-        }
-        // rest of this block column
-        add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+        int w = std::min(nb, nd.n - A.bcol_c[g] * nb);
+        maxsteps = std::max(maxsteps, cdiv(w, IB));
       }
-      if ((i64)A.potrf_tasks.size() > p0)
-        A.launches.push_back({L_POTRF, d, p0, (i64)A.potrf_tasks.size() - p0});
-      if ((i64)A.trsm_tasks.size() > t0)
-        A.launches.push_back({L_TRSM, d, t0, (i64)A.trsm_tasks.size() - t0});
-      flush_tiles(d);
+      for (int p = 0; p < maxsteps; ++p) {
+        i64 p0 = A.panel_tasks.size();
+        for (int g : at[d]) {
+          const HNode& nd = A.nodes[A.bcol_node[g]];
+          int r0 = A.bcol_c[g] * nb;
+          int w = std::min(nb, nd.n - r0);
+          if (p * IB >= w) continue;
+          int pw = std::min(IB, w - p * IB);
+          int k0 = r0 + p * IB;
+          PanelTask pt;
+          pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
+          pt.ld = nd.ld;
+          pt.pw = pw;
+          pt.col0 = nd.sa + k0;
+          pt.pad = 0;
+          int r = k0 + pw;
+          bool first = true;
+          do {
+            pt.r_off = nd.off + (i64)r * nd.ld + k0;
+            pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
+            pt.first = first ? 1 : 0;
+            A.panel_tasks.push_back(pt);
+            first = false;
+            r += TRSM_ROWS;
+          } while (r < nd.m);
+          // rest of this block column
+          add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+        }
+        if ((i64)A.panel_tasks.size() > p0)
+          A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0});
+        flush_tiles(d, 1);
+      }
+      // outer updates of the block columns finished at this depth
+      for (int g : at[d]) {
+        const HNode& nd = A.nodes[A.bcol_node[g]];
+        int c = A.bcol_c[g];
+        int r0 = c * nb;
+        int w = std::min(nb, nd.n - r0);
+        if (c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
+      }
+      flush_tiles(d, 2);
+      for (int g : at[d]) {
+        const HNode& nd = A.nodes[A.bcol_node[g]];
+        if (A.bcol_c[g] + 1 == nd.nc && nd.m > nd.n)
+          add_tiles(A, ts, tl, nd, nd.n, nd.m, 0, nd.m, 0, nd.n, A.bcol_node[g], tile_l_min);
+      }
+      flush_tiles(d, 3);
     }
-    // outer updates of the block columns finished at this depth
-    for (int g : at[d]) {
-      const HNode& nd = A.nodes[A.bcol_node[g]];
-      int c = A.bcol_c[g];
-      int r0 = c * nb;
-      int w = std::min(nb, nd.n - r0);
-      if (c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
-      if (c + 1 == nd.nc && nd.m > nd.n)
-        add_tiles(A, ts, tl, nd, nd.n, nd.m, 0, nd.m, 0, nd.n, A.bcol_node[g], tile_l_min);
-    }
-    flush_tiles(d);
+  }
+}
+
+// Subtree -> GPU mapping.  The pruned subtrees (small == 1 roots, the reference's unit of
+// tree parallelism, src/spllt_analyse_mod.F90:806-987 with nth = number of GPUs) are dealt
+// to ranks largest-first onto the least loaded rank (the same greedy rule the pruning
+// heuristic itself uses to judge balance); the upper tree (small == 0) is shared.
+void partition_tree(Analysis& A, int rank, int world) {
+  A.rank = rank;
+  A.world = world;
+  const int nn = A.nnodes;
+  for (int s = 0; s < nn; ++s) A.nodes[s].owner = (world <= 1) ? 0 : -1;
+  if (world <= 1) return;
+  std::vector<int> roots;
+  for (int s = 0; s < nn; ++s)
+    if (A.nodes[s].small == 1) roots.push_back(s);
+  std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return A.weight[a] > A.weight[b]; });
+  std::vector<i64> load(world, 0);
+  for (int r : roots) {
+    int p = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    load[p] += A.weight[r];
+    for (int k = A.nodes[r].least_desc; k <= r; ++k) A.nodes[k].owner = p;
   }
 }
 

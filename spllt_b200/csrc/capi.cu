@@ -505,6 +505,11 @@ double spllt_b200_tile_flops(void* akeep) { return AA(akeep)->tile_flops; }
 void spllt_b200_launch_breakdown(void* akeep, long long* out4) {
   out4[0] = out4[1] = out4[2] = out4[3] = 0;
   for (const Launch& L : AA(akeep)->launches) out4[L.kind]++;
+  out4[3] = (long long)AA(akeep)->launches.size();
+}
+
+void spllt_b200_profile_factor(void* fkeep, const double* d_val, double* ms4, const char* csv) {
+  EE(fkeep)->profile_factor(d_val, ms4, csv);
 }
 
 double spllt_b200_peak_probe(int kind, int iters, void* stream) {
@@ -522,8 +527,13 @@ void spllt_b200_shared_region(void* akeep, long long* begin, long long* end) {
   *end = AA(akeep)->arena;
 }
 void spllt_b200_partition(void* akeep, void* fkeep, int rank, int world) {
-  (void)akeep; (void)fkeep; (void)rank; (void)world;
+  Analysis* A = AA(akeep);
+  Engine* e = EE(fkeep);
+  e->release();   // work lists change: upload again on next use
+  partition_tree(*A, rank, world);
+  build_factor_schedule(*A, env_int("SPLLT_B200_TILE_L_MIN", 128));
 }
+int spllt_b200_node_owner(void* akeep, int node) { return AA(akeep)->nodes[node - 1].owner; }
 void spllt_b200_factor_phase(void* akeep, void* fkeep, const double* d_val, int phase) {
   (void)akeep;
   Engine* e = EE(fkeep);

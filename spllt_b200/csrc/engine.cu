@@ -70,8 +70,7 @@ void Engine::upload_tables() {
     d_lmap_src = upload(S.lmap_src);
   }
   CK(cudaMalloc(&d_val, std::max<i64>(S.nnz, 1) * sizeof(double)));
-  d_potrf = upload(S.potrf_tasks);
-  d_trsm = upload(S.trsm_tasks);
+  d_panel = upload(S.panel_tasks);
   d_tile = upload(S.tile_tasks);
   d_qbase = upload(S.q_base);
   d_qld = upload(S.q_ld);
@@ -98,25 +97,30 @@ void Engine::ensure_solve_buffers(int nrhs) {
   xw_nrhs = nrhs;
 }
 
+void Engine::launch_one(const Launch& L, cudaStream_t st) {
+  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
+  switch (L.kind) {
+    case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, st); break;
+    case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
+    case L_TILE_L: launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st); break;
+  }
+}
+
 // Enqueue one factorization: zero L, scatter A, then every launch of the level schedule.
-// phase: -1 = everything; 0 = assemble + launches with depth < split; 1 = the rest.
+// phase: -1 = everything; 0 = assemble + the subtrees this rank owns; 1 = shared top of the tree.
 void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
   const Analysis& S = *A;
-  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
   if (phase <= 0) {
     CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
     CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
     launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
+    // several ranks add their contributions to the shared top: only rank 0 keeps A's entries there
+    if (S.world > 1 && S.rank != 0 && S.arena > S.top_begin)
+      CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
   }
   for (const Launch& L : S.launches) {
-    if (phase == 0 && L.depth >= split_depth) continue;
-    if (phase == 1 && L.depth < split_depth) continue;
-    switch (L.kind) {
-      case L_POTRF: launch_potrf(d_potrf + L.begin, L.count, arena, d_info, st); break;
-      case L_TRSM: launch_trsm(d_trsm + L.begin, L.count, arena, st); break;
-      case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
-      case L_TILE_L: launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st); break;
-    }
+    if (phase >= 0 && L.phase != phase) continue;
+    launch_one(L, st);
   }
 }
 
@@ -142,6 +146,49 @@ void Engine::factor(const double* dval) {
     CK(cudaGraphLaunch(factor_graph, stream));
   else
     enqueue_factor(dval, stream, -1);
+  factored = true;
+}
+
+// Un-graphed factorization with one event pair per launch: milliseconds per kernel kind
+// (assemble+memset, panel, tile_s, tile_l) and, optionally, one CSV line per launch.
+void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
+  upload_tables();
+  for (int i = 0; i < 4; ++i) ms4[i] = 0;
+  if (A->n == 0) return;
+  const Analysis& S = *A;
+  std::vector<cudaEvent_t> ev(S.launches.size() + 2);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  cudaStream_t st = stream;
+  CK(cudaEventRecord(ev[0], st));
+  CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
+  CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
+  launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
+  CK(cudaEventRecord(ev[1], st));
+  for (size_t i = 0; i < S.launches.size(); ++i) {
+    launch_one(S.launches[i], st);
+    CK(cudaEventRecord(ev[i + 2], st));
+  }
+  CK(cudaStreamSynchronize(st));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+  ms4[0] = ms;
+  FILE* f = csv ? fopen(csv, "w") : nullptr;
+  if (f) fprintf(f, "launch,kind,tag,depth,ctas,ms,flops_issued\n");
+  for (size_t i = 0; i < S.launches.size(); ++i) {
+    const Launch& L = S.launches[i];
+    CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]));
+    ms4[1 + L.kind] += ms;
+    if (f) {
+      double fl = 0;
+      if (L.kind != L_PANEL) {
+        double T = L.kind == L_TILE_L ? 128.0 : 64.0;
+        for (i64 k = L.begin; k < L.begin + L.count; ++k) fl += 2.0 * T * T * S.tile_tasks[k].kk;
+      }
+      fprintf(f, "%zu,%d,%d,%d,%lld,%.6f,%.0f\n", i, L.kind, L.tag, L.depth, (long long)L.count, ms, fl);
+    }
+  }
+  if (f) fclose(f);
+  for (auto& e : ev) CK(cudaEventDestroy(e));
   factored = true;
 }
 
@@ -250,8 +297,7 @@ void Engine::release() {
   cudaFree(d_lmap_dst);
   cudaFree(d_lmap_src);
   cudaFree(d_val);
-  cudaFree(d_potrf);
-  cudaFree(d_trsm);
+  cudaFree(d_panel);
   cudaFree(d_tile);
   cudaFree(d_qbase);
   cudaFree(d_qld);

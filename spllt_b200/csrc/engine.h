@@ -35,8 +35,7 @@ struct Engine {
   i64* d_lmap_dst = nullptr;
   i64* d_lmap_src = nullptr;
   double* d_val = nullptr;
-  PanelTask* d_potrf = nullptr;
-  TrsmTask* d_trsm = nullptr;
+  PanelTask* d_panel = nullptr;
   TileTask* d_tile = nullptr;
   i64* d_qbase = nullptr;
   int* d_qld = nullptr;
@@ -65,6 +64,8 @@ struct Engine {
   void enqueue_factor(const double* dval, cudaStream_t st, int phase);
   void factor(const double* dval);
   void factor_host(const double* val);
+  void profile_factor(const double* dval, double* ms5, const char* csv);
+  void launch_one(const Launch& L, cudaStream_t st);
   void enqueue_solve(double* dx, int ldx, int nrhs, int job, cudaStream_t st);
   void solve(double* dx, int ldx, int nrhs, int job);
   void solve_host(double* x, int nrhs, int job);

@@ -1,8 +1,8 @@
 // sm_100a kernels of the SpLLT numerical phase.
 //
 //   k_assemble   a10  spllt_init_node          src/spllt_kernels_mod.F90:2301-2364
-//   k_potrf      a1   spllt_factor_diag_block  :1168-1189   (inner panel diagonal block)
-//   k_trsm       a1/a2 spllt_solve_block       :1217-1229   (rows * L_pp^-T)
+//   k_panel      a1   spllt_factor_diag_block  :1168-1189   (inner panel diagonal block)
+//                a2   spllt_solve_block        :1217-1229   (rows * L_pp^-T), fused
 //   k_tile       a3   spllt_update_block       :1261-1292   (intra-node, src < 0)
 //                a4-a7 spllt_update_between + expand_buffer / update_direct
 //                     :2108-2237, :2010-2053, :14-93        (inter-node, fused scatter)
@@ -46,82 +46,126 @@ __global__ void k_assemble(double* __restrict__ arena, const i64* __restrict__ d
   for (; i < cnt; i += stride) arena[dst[i]] = val[src[i]];
 }
 
-// ------------------------------------------------------------------------------ potrf
-constexpr int PLD = IB + 1;
-__global__ void __launch_bounds__(256) k_potrf(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
-                                               int* __restrict__ info) {
-  __shared__ double a[IB * PLD];
+// ------------------------------------------------------------------------------ panel
+// One inner panel: Cholesky of the pw x pw diagonal block + triangular solve of a chunk of rows.
+// Both phases work on 16-column register blocks with run-time outer loops: a fully unrolled
+// 64-column version is ~300 KB of straight-line SASS and runs instruction-fetch bound (measured
+// 67 us per panel); this form is a few thousand instructions.
+// Phase A: thread r owns row r of the diagonal block.  Per 16-column block: left-looking update
+// from the finished columns, then column by column (one barrier each, column published through
+// a double-buffered shared array): a_rj -= (a_rk / a_kk) * a_jk, so only rsqrt sits on the
+// per-column critical path; l_rk = a_rk * rsqrt(a_kk) is produced off it.
+// Phase B: thread r owns one row of the chunk: x_blk -= X_done * L^T (left-looking), then the
+// 16 x 16 diagonal solve.  Column c of L is contiguous in shared memory (Lt is L transposed).
+constexpr int PLD = IB + 1;   // X rows: conflict-free when thread r reads X[r][c]
+constexpr int LTD = IB + 2;   // Lt rows: even, so (c*LTD + j) is 16-byte aligned for even j
+constexpr int PB = 16;        // register block
+constexpr int SMEM_PANEL = (IB * LTD + TRSM_ROWS * PLD + 2 * IB + IB) * 8;
+
+__global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
+                                                      int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* Lt = sm;                        // [IB][LTD]   Lt[c][r] = L[r][c]
+  double* X = Lt + IB * LTD;              // [TRSM_ROWS][PLD]  (first holds the staged diagonal block)
+  double* col = X + TRSM_ROWS * PLD;      // [2][IB]
+  double* dinv = col + 2 * IB;            // [IB]
   const PanelTask t = tasks[blockIdx.x];
   const int pw = t.pw, tid = threadIdx.x;
-  double* g = arena + t.d_off;
-  for (int idx = tid; idx < pw * pw; idx += 256) {
-    int r = idx / pw, c = idx - r * pw;
-    a[r * PLD + c] = (c <= r) ? g[(i64)r * t.ld + c] : 0.0;
-  }
-  for (int k = 0; k < pw; ++k) {
-    __syncthreads();
-    double akk = a[k * PLD + k];
-    if (!(akk > 0.0) && tid == 0) atomicMin(info, t.col0 + k + 1);
-    double d = sqrt(akk);
-    __syncthreads();
-    if (tid == 0) a[k * PLD + k] = d;
-    int i = k + 1 + tid;
-    if (i < pw) a[i * PLD + k] /= d;
-    __syncthreads();
-    int nt = pw - k - 1;
-    for (int idx = tid; idx < nt * nt; idx += 256) {
-      int ii = idx / nt, jj = idx - ii * nt;
-      if (jj <= ii) a[(k + 1 + ii) * PLD + k + 1 + jj] -= a[(k + 1 + ii) * PLD + k] * a[(k + 1 + jj) * PLD + k];
-    }
-  }
-  __syncthreads();
-  for (int idx = tid; idx < pw * pw; idx += 256) {
-    int r = idx / pw, c = idx - r * pw;
-    if (c <= r) g[(i64)r * t.ld + c] = a[r * PLD + c];
-  }
-}
-
-// ------------------------------------------------------------------------------ trsm
-// Each thread owns one row and runs the forward substitution in registers; L_pp is read
-// from shared memory as a broadcast.
-__global__ void __launch_bounds__(TRSM_ROWS) k_trsm(const TrsmTask* __restrict__ tasks, double* __restrict__ arena) {
-  extern __shared__ double sm[];
-  double* Ld = sm;               // [IB][PLD]
-  double* X = sm + IB * PLD;     // [TRSM_ROWS][PLD]
-  const TrsmTask t = tasks[blockIdx.x];
-  const int pw = t.pw, tid = threadIdx.x;
-  const double* gd = arena + t.d_off;
+  double* gd = arena + t.d_off;
   double* gr = arena + t.r_off;
   for (int idx = tid; idx < pw * pw; idx += TRSM_ROWS) {
     int r = idx / pw, c = idx - r * pw;
-    Ld[r * PLD + c] = gd[(i64)r * t.ld + c];
+    X[r * PLD + c] = (c <= r) ? gd[(i64)r * t.ld + c] : 0.0;
   }
+  __syncthreads();
+  const bool rowthread = tid < pw;
+  // ---------------- phase A
+  for (int c0 = 0; c0 < pw; c0 += PB) {
+    double a[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) a[j] = (rowthread && c0 + j < pw && c0 + j <= tid) ? X[tid * PLD + c0 + j] : 0.0;
+    if (rowthread && tid >= c0) {
+      for (int c = 0; c < c0; ++c) {
+        double lrc = Lt[c * LTD + tid];
+        const double2* lc = reinterpret_cast<const double2*>(Lt + c * LTD + c0);
+#pragma unroll
+        for (int j = 0; j < PB / 2; ++j) {
+          double2 l2 = lc[j];
+          a[2 * j] -= lrc * l2.x;
+          a[2 * j + 1] -= lrc * l2.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < PB; ++kk) {
+      const int k = c0 + kk;
+      if (k < pw) {
+        double* cb = col + (kk & 1) * IB;
+        if (rowthread && tid >= k) cb[tid] = a[kk];
+        __syncthreads();
+        if (rowthread && tid >= k) {
+          double akk = cb[k];
+          if (tid == k && t.first && !(akk > 0.0)) atomicMin(info, t.col0 + k + 1);
+          double s = rsqrt(akk);
+          double me = a[kk];
+          Lt[k * LTD + tid] = me * s;
+          if (tid == k) dinv[k] = s;
+          double tt = me * (s * s);
+#pragma unroll
+          for (int jj = kk + 1; jj < PB; ++jj)
+            if (c0 + jj <= tid) a[jj] -= tt * cb[c0 + jj];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---------------- phase B
   for (int idx = tid; idx < t.nrows * pw; idx += TRSM_ROWS) {
     int r = idx / pw, c = idx - r * pw;
     X[r * PLD + c] = gr[(i64)r * t.ld + c];
   }
   __syncthreads();
   if (tid < t.nrows) {
-    double x[IB];
+    double* xr = X + tid * PLD;
+    for (int c0 = 0; c0 < pw; c0 += PB) {
+      double x[PB];
 #pragma unroll
-    for (int c = 0; c < IB; ++c) x[c] = (c < pw) ? X[tid * PLD + c] : 0.0;
+      for (int j = 0; j < PB; ++j) x[j] = (c0 + j < pw) ? xr[c0 + j] : 0.0;
+      for (int c = 0; c < c0; ++c) {
+        double xc = xr[c];
+        const double2* lc = reinterpret_cast<const double2*>(Lt + c * LTD + c0);
 #pragma unroll
-    for (int c = 0; c < IB; ++c) {
-      if (c < pw) {
-        double s = x[c];
-#pragma unroll
-        for (int k = 0; k < c; ++k) s -= x[k] * Ld[c * PLD + k];
-        x[c] = s / Ld[c * PLD + c];
+        for (int j = 0; j < PB / 2; ++j) {
+          double2 l2 = lc[j];
+          x[2 * j] -= xc * l2.x;
+          x[2 * j + 1] -= xc * l2.y;
+        }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < IB; ++c)
-      if (c < pw) X[tid * PLD + c] = x[c];
+      for (int kk = 0; kk < PB; ++kk) {
+        if (c0 + kk < pw) {
+          double xc = x[kk] * dinv[c0 + kk];
+          x[kk] = xc;
+          const double* lc = Lt + (c0 + kk) * LTD + c0;
+#pragma unroll
+          for (int jj = kk + 1; jj < PB; ++jj) x[jj] -= xc * lc[jj];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PB; ++j)
+        if (c0 + j < pw) xr[c0 + j] = x[j];
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < t.nrows * pw; idx += TRSM_ROWS) {
     int r = idx / pw, c = idx - r * pw;
     gr[(i64)r * t.ld + c] = X[r * PLD + c];
+  }
+  if (t.first) {
+    for (int idx = tid; idx < pw * pw; idx += TRSM_ROWS) {
+      int r = idx / pw, c = idx - r * pw;
+      if (c <= r) gd[(i64)r * t.ld + c] = Lt[c * LTD + r];
+    }
   }
 }
 
@@ -488,7 +532,6 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const SolveBcol* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------ launchers
-constexpr int SMEM_TRSM = (IB * PLD + TRSM_ROWS * PLD) * 8;
 constexpr int SMEM_TILE_S = NSTAGE * (64 + 64) * SLD * 8;
 constexpr int SMEM_TILE_L = NSTAGE * (128 + 128) * SLD * 8;
 constexpr int SMEM_SOLVE_MAX = 200 * 1024;
@@ -503,7 +546,7 @@ constexpr int SMEM_SOLVE_MAX = 200 * 1024;
   } while (0)
 
 void kernels_init() {
-  CK(cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TRSM));
+  CK(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
   CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
   CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
   CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
@@ -519,11 +562,8 @@ void launch_assemble(double* arena, const i64* dst, const i64* src, const double
   int blocks = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
   k_assemble<<<blocks, 256, 0, st>>>(arena, dst, src, val, cnt);
 }
-void launch_potrf(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st) {
-  if (count > 0) k_potrf<<<(unsigned)count, 256, 0, st>>>(tasks, arena, info);
-}
-void launch_trsm(const TrsmTask* tasks, i64 count, double* arena, cudaStream_t st) {
-  if (count > 0) k_trsm<<<(unsigned)count, TRSM_ROWS, SMEM_TRSM, st>>>(tasks, arena);
+void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st) {
+  if (count > 0) k_panel<<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info);
 }
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
   if (count <= 0) return;

@@ -49,18 +49,16 @@ struct HNode {
 };
 
 // ------------------------------------------------------------------ device work lists
-// Factorization of one inner panel's diagonal block (a1, src/spllt_kernels_mod.F90:1168).
+// One inner panel of a block column (a1 + a2, src/spllt_kernels_mod.F90:1168-1189, :1217-1229):
+// every CTA factorizes the pw x pw diagonal block in shared memory (redundantly -- it is on
+// the critical path anyway and this saves a launch) and then solves its own chunk of rows,
+//   rows <- rows * L_pp^-T.   The CTA with `first` set also stores L_pp.
 struct PanelTask {
   i64 d_off;         // arena offset of the pw x pw diagonal block
-  int ld, pw;
+  i64 r_off;         // first row of this chunk (below the diagonal block)
+  int ld, pw, nrows;
   int col0;          // global pivot column of the panel's first column (error report)
-  int pad;
-};
-// Panel solve rows <- rows * L_pp^-T  (a1 trapezoid part + a2, :1179-1186, :1217-1229).
-struct TrsmTask {
-  i64 d_off;         // diagonal block
-  i64 r_off;         // first row of this chunk
-  int ld, pw, nrows, pad;
+  int first, pad;
 };
 // One dense tile update (a3 intra-node, a4 inter-node):
 //   C[i, j] -= sum_{k in [k0, k0+kk)} L[i, k] * L[j, k],  i in [i0,i0+mt), j in [j0,j0+nt), i >= j
@@ -75,12 +73,14 @@ struct TileTask {
   i64 qoff;          // row_base - n of the source (index of row r in the maps = qoff + r)
 };
 
-enum LaunchKind { L_POTRF = 0, L_TRSM = 1, L_TILE_S = 2, L_TILE_L = 3 };
+enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_NKIND = 3 };
 struct Launch {
   int kind;
   int depth;
   i64 begin;         // first task in the list of this kind
   i64 count;         // tasks (= CTAs)
+  int phase;         // multi-GPU: 0 = subtrees owned by this rank, 1 = shared top of the tree
+  int tag;           // diagnostics: 0 panel, 1 inner update (K = IB), 2 outer intra-node, 3 inter-node
 };
 
 // ------------------------------------------------------------------ solve work lists
@@ -111,6 +111,7 @@ struct RefBlock {    // spllt_block, 1-based (src/spllt_data_mod.F90:123-172)
 
 struct Analysis {
   int n = 0, nb = 0, nemin = 32, ncpu = 1, prune = 1, min_width_blas = 8;
+  int rank = 0, world = 1;   // multi-GPU partition (partition_tree)
   i64 nnz = 0;               // entries of the user's lower triangle
   Symbolic sym;
   std::vector<int> porder;   // porder[p] = variable at pivot position p (0-based both)
@@ -136,8 +137,7 @@ struct Analysis {
   i64 num_flops = 0;               // sum_nodes sum_j (m-n+j)^2  (akeep%weight(nnodes+1))
 
   // factor schedule
-  std::vector<PanelTask> potrf_tasks;
-  std::vector<TrsmTask> trsm_tasks;
+  std::vector<PanelTask> panel_tasks;
   std::vector<TileTask> tile_tasks;
   std::vector<Launch> launches;
   std::vector<i64> q_base;         // per below-diagonal row: dest address when used as a COLUMN
@@ -156,6 +156,7 @@ struct Analysis {
 int build_analysis(int n, const int* ptr, const int* row, int nb, int nemin, int ncpu, int prune,
                    int ordering, const int* user_order, Analysis& A);
 void prune_tree(Analysis& A, int nth, std::vector<int>& small);
+void partition_tree(Analysis& A, int rank, int world);
 void build_factor_schedule(Analysis& A, int tile_l_min);
 void build_solve_schedule(Analysis& A);
 void ref_blocks(const Analysis& A, std::vector<RefBlock>& out);

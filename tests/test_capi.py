@@ -1,0 +1,83 @@
+"""The C-ABI shared library loads and exports every symbol include/*.h declares; host-only entry
+points behave like the reference's (no compute calls here: there is no GPU on the CPU box)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+import spllt_b200 as sp
+from spllt_b200 import matrices as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = []
+    for h in ("spllt_iface.h", "spllt_b200.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names += re.findall(r"\b(spllt_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    L = sp.load_library()
+    names = declared_symbols()
+    assert len(names) >= 40
+    for nme in names:
+        assert hasattr(L, nme), nme
+    # and the ctypes mirror binds all of them
+    assert set(names) <= set(L._signatures), set(names) - set(L._signatures)
+
+
+def test_struct_layouts_match_reference_header():
+    assert C.sizeof(sp.Options) == 14 * 4      # include/spllt_iface.h:14-31
+    assert C.sizeof(sp.Inform) == 6 * 4        # :49-57
+    assert [f[0] for f in sp.Options._fields_][:4] == ["print_level", "nrhs", "ncpu", "nb"]
+
+
+def test_analyse_is_host_only_and_fills_inform():
+    n, ptr, row, val = M.poisson2d(10)
+    s = sp.SpLLT(nb=8)
+    assert s.analyse(n, ptr, row) == 0
+    assert s.info.num_nodes == s.nnodes > 0
+    assert s.info.num_factor == s.num_factor and s.info.num_flops == s.num_flops
+    assert sorted(s.order[:n]) == list(range(1, n + 1))
+    ws = s.prepare_solve_size(3)
+    sptr, sparent, rptr, rlist = s.symbolic()
+    assert ws == 3 * int(np.sum(np.diff(rptr) - np.diff(sptr)))
+    size = C.c_long(0)
+    s.L.spllt_solve_workspace_size(s.fkeep, 2, 3, C.byref(size))       # src/spllt_data_mod.F90:655
+    assert size.value == n * 3 + (s.L.spllt_b200_maxmn(s.akeep) + n) * 3 * 2
+    s.free()
+    assert s.akeep.value is None and s.fkeep.value is None
+
+
+def test_invalid_job_needs_no_gpu():
+    n, ptr, row, val = M.poisson2d(6)
+    s = sp.SpLLT(nb=8)
+    s.analyse(n, ptr, row)
+    x = np.ones(n)
+    assert s.solve(x, 7) == -10        # SPLLT_WARNING_PARAM_VALUE, src/spllt_solve_mod.F90:216-220
+    assert np.all(x == 1.0)
+
+
+def test_task_manager_handles():
+    L = sp.lib()
+    tm, st = C.c_void_p(None), C.c_int(5)
+    L.spllt_task_manager_init(C.byref(tm))
+    assert tm.value
+    L.spllt_task_manager_deallocate(C.byref(tm), C.byref(st))
+    assert tm.value is None and st.value == 0
+
+
+def test_user_and_natural_ordering():
+    n, ptr, row, val = M.poisson2d(7)
+    s = sp.SpLLT(nb=8)
+    s.analyse(n, ptr, row, ordering=sp.ORDER_NATURAL)
+    assert np.array_equal(np.sort(s.order[:n]), np.arange(1, n + 1))
+    perm = np.random.default_rng(3).permutation(n).astype(np.int32) + 1
+    s2 = sp.SpLLT(nb=8)
+    s2.analyse(n, ptr, row, ordering=sp.ORDER_USER, order=perm)
+    assert sorted(s2.order[:n]) == list(range(1, n + 1))
