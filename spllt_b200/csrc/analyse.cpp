@@ -323,38 +323,47 @@ void ref_blocks(const Analysis& A, std::vector<RefBlock>& out) {
 // then one "outer" launch group applies the finished block columns to
 //   * the later block columns of the same node (a3, K = width of the block column), and
 //   * if the node is complete, to its ancestors (a4, K = n, scatter through q_* maps).
-static void add_tiles(Analysis& A, std::vector<TileTask>& small, std::vector<TileTask>& large,
-                      const HNode& nd, int jbeg, int jend, int ibeg_min, int iend, int k0, int kk,
-                      int src, int tile_l_min) {
-  // region: columns (B rows) j in [jbeg, jend), rows i in [max(j, ibeg_min), iend), lower part
-  if (jend <= jbeg || iend <= jbeg) return;
-  i64 area = (i64)(jend - jbeg) * (iend - std::max(jbeg, ibeg_min));
-  bool big = (jend - jbeg) >= tile_l_min && (iend - jbeg) >= tile_l_min && area >= (i64)128 * 128 && kk >= 16;
-  const int T = big ? 128 : 64;
-  std::vector<TileTask>& dst = big ? large : small;
-  for (int j0 = jbeg; j0 < jend; j0 += T) {
-    int nt = std::min(T, jend - j0);
-    int istart = std::max(j0, ibeg_min);
-    for (int i0 = istart; i0 < iend; i0 += T) {
+struct Region {       // lower part of columns [jbeg, jend) x rows [max(j, ibeg_min), iend) of one source node
+  const HNode* nd;
+  int jbeg, jend, ibeg_min, iend, k0, kk, src;
+};
+
+static i64 count_tiles(const Region& r, int T) {
+  i64 c = 0;
+  for (int j0 = r.jbeg; j0 < r.jend; j0 += T) {
+    int istart = std::max(j0, r.ibeg_min);
+    if (r.iend > istart) c += (r.iend - istart + T - 1) / T;
+  }
+  return c;
+}
+
+static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r, int T) {
+  const HNode& nd = *r.nd;
+  for (int j0 = r.jbeg; j0 < r.jend; j0 += T) {
+    int nt = std::min(T, r.jend - j0);
+    int istart = std::max(j0, r.ibeg_min);
+    for (int i0 = istart; i0 < r.iend; i0 += T) {
       TileTask t;
       t.off = nd.off;
       t.ld = nd.ld;
       t.i0 = i0;
       t.j0 = j0;
-      t.k0 = k0;
-      t.mt = std::min(T, iend - i0);
+      t.k0 = r.k0;
+      t.mt = std::min(T, r.iend - i0);
       t.nt = nt;
-      t.kk = kk;
-      t.src = src;
+      t.kk = r.kk;
+      t.src = r.src;
       t.qoff = nd.row_base - nd.n;
       dst.push_back(t);
-      A.tile_flops += 2.0 * T * T * kk;
+      A.tile_flops += 2.0 * T * T * r.kk;
     }
   }
 }
 
 void build_factor_schedule(Analysis& A, int tile_l_min) {
   const int nn = A.nnodes, nb = A.nb;
+  const char* tw = getenv("SPLLT_B200_TILE_WAVE");
+  const i64 tile_wave = tw ? atoll(tw) : 148;
   A.panel_tasks.clear();
   A.tile_tasks.clear();
   A.launches.clear();
@@ -396,8 +405,34 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
 
   // ---- level sets, one pass per phase (phase 0: nodes owned by this rank, phase 1: shared top)
   std::vector<TileTask> ts, tl;
+  std::vector<Region> regions;
   int cur_phase = 0;
+  auto add_tiles = [&](Analysis&, std::vector<TileTask>&, std::vector<TileTask>&, const HNode& nd, int jbeg, int jend,
+                       int ibeg_min, int iend, int k0, int kk, int src, int) {
+    if (jend <= jbeg || iend <= jbeg) return;
+    regions.push_back({&nd, jbeg, jend, ibeg_min, iend, k0, kk, src});
+  };
   auto flush_tiles = [&](int depth, int tag) {
+    // Tile size per launch: 128 x 128 tiles only pay off when the launch fills the machine;
+    // a launch with less than a wave of them is latency bound and runs faster on 64 x 64
+    // tiles spread over more SMs.  Tasks are sorted by decreasing work so the tail of every
+    // launch consists of small tiles.
+    i64 nlarge = 0;
+    std::vector<char> big(regions.size(), 0);
+    for (size_t i = 0; i < regions.size(); ++i) {
+      const Region& r = regions[i];
+      big[i] = (r.jend - r.jbeg) >= tile_l_min && (r.iend - r.jbeg) >= tile_l_min && r.kk >= 16;
+      if (big[i]) nlarge += count_tiles(r, 128);
+    }
+    const bool use_large = nlarge >= tile_wave;
+    for (size_t i = 0; i < regions.size(); ++i) {
+      if (use_large && big[i]) emit_tiles(A, tl, regions[i], 128);
+      else emit_tiles(A, ts, regions[i], 64);
+    }
+    regions.clear();
+    auto work = [](const TileTask& t) { return (i64)t.kk * t.mt * t.nt; };
+    std::stable_sort(ts.begin(), ts.end(), [&](const TileTask& a, const TileTask& b) { return work(a) > work(b); });
+    std::stable_sort(tl.begin(), tl.end(), [&](const TileTask& a, const TileTask& b) { return work(a) > work(b); });
     if (!ts.empty()) {
       A.launches.push_back({L_TILE_S, depth, (i64)A.tile_tasks.size(), (i64)ts.size(), cur_phase, tag});
       A.tile_tasks.insert(A.tile_tasks.end(), ts.begin(), ts.end());

@@ -164,11 +164,33 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
   launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
   CK(cudaEventRecord(ev[1], st));
+  long long* dbg = nullptr;
+  const char* dbg_env = getenv("SPLLT_B200_PANEL_DBG");
+  int dbg_launch = dbg_env ? atoi(dbg_env) : -1;
+  i64 dbg_count = 0;
   for (size_t i = 0; i < S.launches.size(); ++i) {
-    launch_one(S.launches[i], st);
+    const Launch& L = S.launches[i];
+    if ((int)i == dbg_launch && L.kind == L_PANEL) {
+      dbg_count = L.count;
+      CK(cudaMalloc(&dbg, dbg_count * 8 * sizeof(long long)));
+      launch_panel_dbg(d_panel + L.begin, L.count, arena, d_info, dbg, st);
+    } else {
+      launch_one(L, st);
+    }
     CK(cudaEventRecord(ev[i + 2], st));
   }
   CK(cudaStreamSynchronize(st));
+  if (dbg) {
+    std::vector<long long> h(dbg_count * 8);
+    CK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (i64 c = 0; c < std::min<i64>(dbg_count, 4); ++c)
+      fprintf(stderr, "panel dbg cta %lld (pw %d nrows %d): load_diag %lld potrf %lld load_rows %lld trsm %lld store %lld\n",
+              (long long)c, S.panel_tasks[S.launches[dbg_launch].begin + c].pw,
+              S.panel_tasks[S.launches[dbg_launch].begin + c].nrows, h[c * 8 + 1] - h[c * 8 + 0],
+              h[c * 8 + 2] - h[c * 8 + 1], h[c * 8 + 3] - h[c * 8 + 2], h[c * 8 + 4] - h[c * 8 + 3],
+              h[c * 8 + 5] - h[c * 8 + 4]);
+    CK(cudaFree(dbg));
+  }
   float ms;
   CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
   ms4[0] = ms;

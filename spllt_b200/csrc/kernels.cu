@@ -62,8 +62,9 @@ constexpr int LTD = IB + 2;   // Lt rows: even, so (c*LTD + j) is 16-byte aligne
 constexpr int PB = 16;        // register block
 constexpr int SMEM_PANEL = (IB * LTD + TRSM_ROWS * PLD + 2 * IB + IB) * 8;
 
+template <bool DBG>
 __global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
-                                                      int* __restrict__ info) {
+                                                      int* __restrict__ info, long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double sm[];
   double* Lt = sm;                        // [IB][LTD]   Lt[c][r] = L[r][c]
   double* X = Lt + IB * LTD;              // [TRSM_ROWS][PLD]  (first holds the staged diagonal block)
@@ -73,11 +74,15 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict
   const int pw = t.pw, tid = threadIdx.x;
   double* gd = arena + t.d_off;
   double* gr = arena + t.r_off;
-  for (int idx = tid; idx < pw * pw; idx += TRSM_ROWS) {
-    int r = idx / pw, c = idx - r * pw;
-    X[r * PLD + c] = (c <= r) ? gd[(i64)r * t.ld + c] : 0.0;
+  // copies: lane -> column (<= 64), two rows per pass, no integer division, loads batched
+  const int cc = tid & (IB - 1), r2 = tid >> 6;
+  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 0] = clock64();
+  if (cc < pw) {
+#pragma unroll 8
+    for (int r = r2; r < pw; r += 2) X[r * PLD + cc] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
   }
   __syncthreads();
+  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 1] = clock64();
   const bool rowthread = tid < pw;
   // ---------------- phase A
   for (int c0 = 0; c0 < pw; c0 += PB) {
@@ -120,11 +125,13 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict
     __syncthreads();
   }
   // ---------------- phase B
-  for (int idx = tid; idx < t.nrows * pw; idx += TRSM_ROWS) {
-    int r = idx / pw, c = idx - r * pw;
-    X[r * PLD + c] = gr[(i64)r * t.ld + c];
+  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 2] = clock64();
+  if (cc < pw) {
+#pragma unroll 8
+    for (int r = r2; r < t.nrows; r += 2) X[r * PLD + cc] = gr[(i64)r * t.ld + cc];
   }
   __syncthreads();
+  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 3] = clock64();
   if (tid < t.nrows) {
     double* xr = X + tid * PLD;
     for (int c0 = 0; c0 < pw; c0 += PB) {
@@ -157,24 +164,24 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < t.nrows * pw; idx += TRSM_ROWS) {
-    int r = idx / pw, c = idx - r * pw;
-    gr[(i64)r * t.ld + c] = X[r * PLD + c];
-  }
-  if (t.first) {
-    for (int idx = tid; idx < pw * pw; idx += TRSM_ROWS) {
-      int r = idx / pw, c = idx - r * pw;
-      if (c <= r) gd[(i64)r * t.ld + c] = Lt[c * LTD + r];
+  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 4] = clock64();
+  if (cc < pw) {
+#pragma unroll 8
+    for (int r = r2; r < t.nrows; r += 2) gr[(i64)r * t.ld + cc] = X[r * PLD + cc];
+    if (t.first) {
+#pragma unroll 8
+      for (int r = r2; r < pw; r += 2)
+        if (cc <= r) gd[(i64)r * t.ld + cc] = Lt[cc * LTD + r];
     }
   }
+  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 5] = clock64();
 }
 
 // ------------------------------------------------------------------------------ tile update
-constexpr int KC = 16;          // K chunk per pipeline stage
+constexpr int KC = 32;          // K chunk per pipeline stage
 constexpr int SLD = KC + 4;     // padded shared row: (r*SLD + k) mod 16 distinct for r<4, k<4
-constexpr int NSTAGE = 3;
 
-template <int BM, int BN, int WM, int WN>
+template <int BM, int BN, int WM, int WN, int NSTAGE>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
     k_tile(const TileTask* __restrict__ tasks, double* __restrict__ arena, DevMaps mp) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -254,29 +261,72 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   cp_wait<0>();
   if (!active) return;
 
+  // Epilogue.  All loads of a batch are issued before the first store / atomic of that batch:
+  // a naive `*c -= v` per element serialises 64 global round trips per thread (measured: 27 us
+  // of a 36 us K = 64 tile).
   const bool scatter = t.src >= 0;
+  const int li = lane >> 2, lj = 2 * (lane & 3);
+  if (!scatter) {
+    double* cbase = arena + t.off;
 #pragma unroll
-  for (int i = 0; i < FM; ++i) {
-    int ii = wm0 + i * 8 + (lane >> 2);
-    if (ii >= t.mt) continue;
-    int gi = t.i0 + ii;
+    for (int i = 0; i < FM; i += 2) {
+      double cv[2][FN][2];
 #pragma unroll
-    for (int j = 0; j < FN; ++j) {
+      for (int u = 0; u < 2; ++u) {
+        int ii = wm0 + (i + u) * 8 + li, gi = t.i0 + ii;
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            int jj = wn0 + j * 8 + lj + e, gj = t.j0 + jj;
+            bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+            cv[u][j][e] = ok ? cbase[(i64)gi * t.ld + gj] : 0.0;
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int ii = wm0 + (i + u) * 8 + li, gi = t.i0 + ii;
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            int jj = wn0 + j * 8 + lj + e, gj = t.j0 + jj;
+            bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+            if (ok) cbase[(i64)gi * t.ld + gj] = cv[u][j][e] - acc[i + u][j][e];
+          }
+      }
+    }
+  } else {
+    // per-thread destination columns are the same for every row block: fetch their maps once
+    i64 qb[FN][2], qr[FN][2];
+    int ql[FN][2];
+#pragma unroll
+    for (int j = 0; j < FN; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        int jj = wn0 + j * 8 + 2 * (lane & 3) + e;
-        int gj = t.j0 + jj;
-        if (jj >= t.nt || gi < gj) continue;
-        double v = acc[i][j][e];
-        if (!scatter) {
-          double* c = arena + t.off + (i64)gi * t.ld + gj;
-          *c -= v;
-        } else {
-          i64 q = t.qoff + gj;
-          double* c = arena + mp.q_base[q] + (i64)mp.rowpos[mp.q_rp[q] + gi] * mp.q_ld[q];
-          atomicAdd(c, -v);
-        }
+        int jj = wn0 + j * 8 + lj + e;
+        i64 q = t.qoff + t.j0 + min(jj, t.nt - 1);
+        qb[j][e] = mp.q_base[q];
+        qr[j][e] = mp.q_rp[q];
+        ql[j][e] = mp.q_ld[q];
       }
+#pragma unroll
+    for (int i = 0; i < FM; ++i) {
+      int ii = wm0 + i * 8 + li, gi = t.i0 + min(ii, t.mt - 1);
+      int rp[FN][2];
+#pragma unroll
+      for (int j = 0; j < FN; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int jj = wn0 + j * 8 + lj + e, gj = t.j0 + jj;
+          bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+          rp[j][e] = ok ? mp.rowpos[qr[j][e] + gi] : -1;
+        }
+#pragma unroll
+      for (int j = 0; j < FN; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (rp[j][e] >= 0) atomicAdd(arena + qb[j][e] + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
     }
   }
 }
@@ -532,8 +582,8 @@ __global__ void __launch_bounds__(256) k_bwd_diag(const SolveBcol* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------ launchers
-constexpr int SMEM_TILE_S = NSTAGE * (64 + 64) * SLD * 8;
-constexpr int SMEM_TILE_L = NSTAGE * (128 + 128) * SLD * 8;
+constexpr int SMEM_TILE_S = 2 * (64 + 64) * SLD * 8;
+constexpr int SMEM_TILE_L = 3 * (128 + 128) * SLD * 8;
 constexpr int SMEM_SOLVE_MAX = 200 * 1024;
 
 #define CK(x)                                                                             \
@@ -546,9 +596,10 @@ constexpr int SMEM_SOLVE_MAX = 200 * 1024;
   } while (0)
 
 void kernels_init() {
-  CK(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
-  CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
-  CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
+  CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
+  CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
+  CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
+  CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
   CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_bwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
@@ -563,14 +614,18 @@ void launch_assemble(double* arena, const i64* dst, const i64* src, const double
   k_assemble<<<blocks, 256, 0, st>>>(arena, dst, src, val, cnt);
 }
 void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st) {
-  if (count > 0) k_panel<<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info);
+  if (count > 0) k_panel<false><<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info, nullptr);
+}
+// diagnostic: runs the panel kernel with clock64() stamps at its phase boundaries (8 per CTA)
+void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, long long* dbg, cudaStream_t st) {
+  if (count > 0) k_panel<true><<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info, dbg);
 }
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
   if (count <= 0) return;
   if (large)
-    k_tile<128, 128, 64, 32><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
+    k_tile<128, 128, 64, 32, 3><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
   else
-    k_tile<64, 64, 32, 32><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
+    k_tile<64, 64, 32, 32, 2><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
 }
 
 void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st) {
