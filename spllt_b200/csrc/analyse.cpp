@@ -354,6 +354,8 @@ static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r,
       t.kk = r.kk;
       t.src = r.src;
       t.qoff = nd.row_base - nd.n;
+      t.node = (int)(&nd - A.nodes.data());
+      t.pad = 0;
       dst.push_back(t);
       A.tile_flops += 2.0 * T * T * r.kk;
     }

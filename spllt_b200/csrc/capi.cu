@@ -514,6 +514,7 @@ void spllt_b200_profile_factor(void* fkeep, const double* d_val, double* ms4, co
 
 double spllt_b200_peak_probe(int kind, int iters, void* stream) {
   require_gpu();
+  if (kind >= 10) return launch_dmma_warps(iters, kind - 10, (cudaStream_t)stream);
   return kind == 0 ? launch_dmma_peak(iters, (cudaStream_t)stream) : launch_dfma_peak(iters, (cudaStream_t)stream);
 }
 

@@ -4,6 +4,8 @@
 // (src/spllt_stf_mod.F90:18-192, src/spllt_solve_mod.F90:244-411).
 #include "engine.h"
 
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +79,42 @@ void Engine::upload_tables() {
   d_qrp = upload(S.q_rp);
   d_rowpos = upload(S.rowpos);
   CK(cudaMalloc(&d_info, sizeof(int)));
+  CK(cudaMalloc(&d_counters, std::max<size_t>(S.launches.size(), 1) * sizeof(int)));
+  use_tma = (S.nb % 2 == 0) && !getenv("SPLLT_B200_NO_TMA");
+  if (use_tma) {
+    // one 2-D tensor map per supernode: the node's m x ld row-major matrix, box = 16 k x 128 rows,
+    // 128-byte swizzle.  The encoder lives in libcuda; fetch it through the runtime so that the
+    // library still loads (for host-only analysis) on machines without a driver.
+    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      fprintf(stderr, "spllt_b200: cuTensorMapEncodeTiled not available\n");
+      abort();
+    }
+    encode_t encode = (encode_t)fn;
+    std::vector<CUtensorMap> maps(std::max(S.nnodes, 1));
+    for (int k = 0; k < S.nnodes; ++k) {
+      const HNode& nd = S.nodes[k];
+      cuuint64_t dims[2] = {(cuuint64_t)nd.ld, (cuuint64_t)nd.m};
+      cuuint64_t strides[1] = {(cuuint64_t)nd.ld * 8};
+      cuuint32_t box[2] = {16, 128};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = encode(&maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, arena + nd.off, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "spllt_b200: cuTensorMapEncodeTiled failed (%d) for node %d (m=%d ld=%d)\n", (int)r, k, nd.m,
+                nd.ld);
+        abort();
+      }
+    }
+    CK(cudaMalloc(&d_tmaps, maps.size() * sizeof(CUtensorMap)));
+    CK(cudaMemcpy(d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  }
   d_sb = upload(S.sbcols);
   d_su = upload(S.supds);
   d_index = upload(S.index);
@@ -102,7 +140,12 @@ void Engine::launch_one(const Launch& L, cudaStream_t st) {
   switch (L.kind) {
     case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, st); break;
     case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
-    case L_TILE_L: launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st); break;
+    case L_TILE_L:
+      if (use_tma)   // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
+        launch_tiles_tma(d_tile + L.begin, L.count, d_counters + (&L - A->launches.data()), arena, mp, d_tmaps, st);
+      else
+        launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st);
+      break;
   }
 }
 
@@ -113,6 +156,7 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
   if (phase <= 0) {
     CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
     CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
+    CK(cudaMemsetAsync(d_counters, 0, std::max<size_t>(S.launches.size(), 1) * sizeof(int), st));
     launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
     // several ranks add their contributions to the shared top: only rank 0 keeps A's entries there
     if (S.world > 1 && S.rank != 0 && S.arena > S.top_begin)
@@ -162,6 +206,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   CK(cudaEventRecord(ev[0], st));
   CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
   CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
+  CK(cudaMemsetAsync(d_counters, 0, std::max<size_t>(S.launches.size(), 1) * sizeof(int), st));
   launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
   CK(cudaEventRecord(ev[1], st));
   long long* dbg = nullptr;
@@ -326,6 +371,9 @@ void Engine::release() {
   cudaFree(d_qrp);
   cudaFree(d_rowpos);
   cudaFree(d_info);
+  cudaFree(d_counters);
+  if (d_tmaps) cudaFree(d_tmaps);
+  d_tmaps = nullptr;
   cudaFree(d_sb);
   cudaFree(d_su);
   cudaFree(d_index);

@@ -42,6 +42,9 @@ struct Engine {
   i64* d_qrp = nullptr;
   int* d_rowpos = nullptr;
   int* d_info = nullptr;
+  int* d_counters = nullptr;  // one tile counter per launch (persistent TMA tile kernel)
+  bool use_tma = true;
+  void* d_tmaps = nullptr;    // CUtensorMap[nnodes] in device memory (128 bytes each)
   SolveBcol* d_sb = nullptr;
   SolveUpd* d_su = nullptr;
   int* d_index = nullptr;

@@ -331,6 +331,257 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
   }
 }
 
+// ------------------------------------------------------------------------------ persistent TMA tile kernel
+// Warp-specialised, persistent version of the 128 x 128 tile update for launches that fill
+// the machine.  One CTA per SM, three warpgroups (register file re-partitioned with
+// setmaxnreg): the producer warp draws tile indices from a global counter (tiles are sorted by
+// decreasing work: a dynamic LPT schedule) and streams the A / B row panels of each K chunk
+// into a ring of shared-memory stages with 2-D tensor-map TMA loads (cp.async.bulk.tensor,
+// SASS UTMALDG; one 16 k x 128 row box = 16 KB per instruction, 128-byte swizzle) that
+// complete on the stage's mbarrier.  The 8 consumer warps wait on the stage, issue DMMA.8x8x4
+// from it and release it; while they run the scatter / RMW epilogue of a tile the producer is
+// already prefetching the next tile.  (1-D bulk copies of 256-byte rows were measured first:
+// ~64 cycles per row copy, slower than cp.async.)
+// The 128B swizzle XORs the 16-byte chunk index with (row % 8); fragment row rho of an 8-row
+// group is read from shared row sigma(rho) = {0,2,4,6,1,3,5,7}, which makes the 8-byte fragment
+// loads of a half-warp hit 16 distinct bank pairs.
+constexpr int TM_ST = 3;
+constexpr int TM_BOXK = 16;                              // doubles per box row (128 bytes)
+constexpr int TM_BOX = 128 * TM_BOXK;                    // doubles per box (16 KB)
+constexpr int TM_STAGE = 4 * TM_BOX;                     // A lo, A hi, B lo, B hi  (KC = 32)
+constexpr int SMEM_TILE_TMA = TM_ST * TM_STAGE * 8 + 1024 + 256;
+static_assert(KC == 2 * TM_BOXK, "stage = two boxes per operand");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 2-D tiled TMA load: box (c0 .. c0+16, c1 .. c1+128) of the tensor described by `tmap`
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct StageHdr {   // what a filled stage contains
+  int tile;         // task index, -1 = no more work
+  int chunk;        // K chunk index inside the tile
+  int last;         // 1 if this is the tile's last chunk
+  int valid;        // valid k in this chunk (<= KC)
+};
+
+__global__ void __launch_bounds__(384, 1)
+    k_tile_tma(const TileTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, double* __restrict__ arena,
+               DevMaps mp, const unsigned char* __restrict__ tmaps) {
+  constexpr int BM = 128, BN = 128, WM = 64, WN = 32, FM = WM / 8, FN = WN / 8;
+  extern __shared__ __align__(16) double sm_raw[];
+  // the swizzle pattern is a function of the shared address: boxes must start 1024-byte aligned
+  double* sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + TM_ST * TM_STAGE);
+  unsigned long long* empty = full + TM_ST;
+  StageHdr* hdr = reinterpret_cast<StageHdr*>(empty + TM_ST);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < TM_ST; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // 3 warpgroups: two of consumers, one for the producer (only its first warp works).  The
+  // register file is re-partitioned between them: 168 regs/thread at launch (384 threads).
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp != 8) return;
+    // ------------------------------------------------ producer
+    int it = 0;  // stages filled so far
+    for (;;) {
+      int ti = 0;
+      if (lane == 0) ti = atomicAdd(counter, 1);
+      ti = __shfl_sync(FULL, ti, 0);
+      if (ti >= ntasks) {
+        int s = it % TM_ST;
+        if (it >= TM_ST) mbar_wait(empty + s, ((it / TM_ST) - 1) & 1);
+        if (lane == 0) {
+          hdr[s] = StageHdr{-1, 0, 1, 0};
+          mbar_arrive(full + s);
+        }
+        break;
+      }
+      const TileTask t = tasks[ti];
+      const unsigned char* tm = tmaps + (size_t)t.node * 128;
+      const int nch = (t.kk + KC - 1) / KC;
+      for (int ch = 0; ch < nch; ++ch, ++it) {
+        int s = it % TM_ST;
+        if (it >= TM_ST) mbar_wait(empty + s, ((it / TM_ST) - 1) & 1);
+        if (lane == 0) {
+          hdr[s] = StageHdr{ti, ch, ch == nch - 1, min(KC, t.kk - ch * KC)};
+          mbar_expect_tx(full + s, TM_STAGE * 8);
+          double* st = sm + s * TM_STAGE;
+          int kc = t.k0 + ch * KC;
+          tma_load_2d(st, tm, kc, t.i0, full + s);
+          tma_load_2d(st + TM_BOX, tm, kc + TM_BOXK, t.i0, full + s);
+          tma_load_2d(st + 2 * TM_BOX, tm, kc, t.j0, full + s);
+          tma_load_2d(st + 3 * TM_BOX, tm, kc + TM_BOXK, t.j0, full + s);
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------- consumers
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
+  const int rho = lane >> 2, lk = lane & 3;
+  // fragment row / column rho of an 8-group is read from shared row sigma(rho) (see header):
+  // this lane's accumulator rows are 8 i + sg(rho), its two columns 8 j + sg(2 lk + e)
+  auto sg = [](int x) { return ((x & 3) << 1) | (x >> 2); };
+  const int sig = sg(rho), li = sig;
+  const int cj0 = sg(2 * lk), cj1 = sg(2 * lk + 1);
+  double acc[FM][FN][2];
+  int it = 0;
+  for (;;) {
+    int s = it % TM_ST;
+    mbar_wait(full + s, (it / TM_ST) & 1);
+    const StageHdr h = hdr[s];
+    if (h.tile < 0) break;
+    const TileTask t = tasks[h.tile];
+    if (h.chunk == 0) {
+#pragma unroll
+      for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    const bool active = (t.i0 + wm0 + WM - 1 >= t.j0 + wn0) && (wm0 < t.mt) && (wn0 < t.nt);
+    if (active) {
+      const double* a = sm + s * TM_STAGE + (wm0 + sig) * TM_BOXK + (lk & 1);
+      const double* b = sm + s * TM_STAGE + 2 * TM_BOX + (wn0 + sig) * TM_BOXK + (lk & 1);
+      const int hsel = lk >> 1;
+      if (h.valid == KC) {
+#pragma unroll
+        for (int k4 = 0; k4 < KC; k4 += 4) {
+          const int x = (k4 >> 4) * TM_BOX + (((((k4 & 15) >> 1) | hsel) ^ sig) << 1);
+          double af[FM], bf[FN];
+#pragma unroll
+          for (int i = 0; i < FM; ++i) af[i] = a[i * 8 * TM_BOXK + x];
+#pragma unroll
+          for (int j = 0; j < FN; ++j) bf[j] = b[j * 8 * TM_BOXK + x];
+#pragma unroll
+          for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      } else {
+        for (int k4 = 0; k4 < h.valid; k4 += 4) {
+          const bool kok = k4 + lk < h.valid;
+          const int x = (k4 >> 4) * TM_BOX + (((((k4 & 15) >> 1) | hsel) ^ sig) << 1);
+          double af[FM], bf[FN];
+#pragma unroll
+          for (int i = 0; i < FM; ++i) af[i] = kok ? a[i * 8 * TM_BOXK + x] : 0.0;
+#pragma unroll
+          for (int j = 0; j < FN; ++j) bf[j] = kok ? b[j * 8 * TM_BOXK + x] : 0.0;
+#pragma unroll
+          for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    ++it;
+    if (!h.last || !active) continue;
+
+    // epilogue (see k_tile): all loads of a batch before its stores / atomics
+    if (t.src < 0) {
+      double* cbase = arena + t.off;
+#pragma unroll
+      for (int i = 0; i < FM; i += 2) {
+        double cv[2][FN][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int ii = wm0 + (i + u) * 8 + li, gi = t.i0 + ii;
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
+              bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+              cv[u][j][e] = ok ? cbase[(i64)gi * t.ld + gj] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int ii = wm0 + (i + u) * 8 + li, gi = t.i0 + ii;
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
+              bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+              if (ok) cbase[(i64)gi * t.ld + gj] = cv[u][j][e] - acc[i + u][j][e];
+            }
+        }
+      }
+    } else {
+      i64 qb[FN][2], qr[FN][2];
+      int ql[FN][2];
+#pragma unroll
+      for (int j = 0; j < FN; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int jj = wn0 + j * 8 + (e ? cj1 : cj0);
+          i64 q = t.qoff + t.j0 + min(jj, t.nt - 1);
+          qb[j][e] = mp.q_base[q];
+          qr[j][e] = mp.q_rp[q];
+          ql[j][e] = mp.q_ld[q];
+        }
+#pragma unroll
+      for (int i = 0; i < FM; ++i) {
+        int ii = wm0 + i * 8 + li, gi = t.i0 + min(ii, t.mt - 1);
+        int rp[FN][2];
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
+            bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+            rp[j][e] = ok ? mp.rowpos[qr[j][e] + gi] : -1;
+          }
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (rp[j][e] >= 0) atomicAdd(arena + qb[j][e] + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ peak probes
 __global__ void __launch_bounds__(256) k_dmma_peak(int iters, double* sink) {
   double acc[16][2];
@@ -600,6 +851,7 @@ void kernels_init() {
   CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
   CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
   CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
+  CK(cudaFuncSetAttribute(k_tile_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_TMA));
   CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_bwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
@@ -619,6 +871,13 @@ void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, c
 // diagnostic: runs the panel kernel with clock64() stamps at its phase boundaries (8 per CTA)
 void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, long long* dbg, cudaStream_t st) {
   if (count > 0) k_panel<true><<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info, dbg);
+}
+void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
+                      const void* tmaps, cudaStream_t st) {
+  if (count <= 0) return;
+  unsigned grid = (unsigned)std::min<i64>(count, 148);
+  k_tile_tma<<<grid, 384, SMEM_TILE_TMA, st>>>(tasks, (int)count, counter, arena, maps,
+                                               (const unsigned char*)tmaps);
 }
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
   if (count <= 0) return;
@@ -674,11 +933,21 @@ void launch_bwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const do
 }
 
 static double* g_sink = nullptr;
+// kind 0: DMMA, full occupancy (8 CTAs x 8 warps per SM); kind 1: DFMA, full occupancy;
+// kind 10 + w: DMMA with exactly w warps per SM (one CTA per SM) -- how many resident warps
+// the FP64 tensor pipe needs to stay busy.
 double launch_dmma_peak(int iters, cudaStream_t st) {
   if (!g_sink) CK(cudaMalloc(&g_sink, 64));
   int blocks = 148 * 8;
   k_dmma_peak<<<blocks, 256, 0, st>>>(iters, g_sink);
   return (double)blocks * 8 * (double)iters * 16 * 512.0;
+}
+double launch_dmma_warps(int iters, int warps, cudaStream_t st) {
+  if (!g_sink) CK(cudaMalloc(&g_sink, 64));
+  // warps per SM = CTAs of 4 warps (one warp per SM sub-partition each)
+  int per_sm = (warps + 3) / 4;
+  k_dmma_peak<<<148 * per_sm, 128, 0, st>>>(iters, g_sink);
+  return 148.0 * per_sm * 4 * (double)iters * 16 * 512.0;
 }
 double launch_dfma_peak(int iters, cudaStream_t st) {
   if (!g_sink) CK(cudaMalloc(&g_sink, 64));

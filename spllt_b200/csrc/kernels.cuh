@@ -19,6 +19,9 @@ void launch_assemble(double* arena, const i64* dst, const i64* src, const double
 void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st);
 void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, long long* dbg, cudaStream_t st);
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st);
+// persistent warp-specialised TMA variant of the 128 x 128 tiles; *counter must be 0 at launch
+void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
+                      const void* tmaps, cudaStream_t st);
 
 // solve
 void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st);
@@ -34,5 +37,6 @@ void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double
 // Returns flops issued; time it with events.
 double launch_dmma_peak(int iters, cudaStream_t st);
 double launch_dfma_peak(int iters, cudaStream_t st);
+double launch_dmma_warps(int iters, int warps, cudaStream_t st);
 
 }  // namespace spllt

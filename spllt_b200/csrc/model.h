@@ -71,6 +71,7 @@ struct TileTask {
   int mt, nt, kk;
   int src;
   i64 qoff;          // row_base - n of the source (index of row r in the maps = qoff + r)
+  int node, pad;     // source node (selects its TMA tensor map)
 };
 
 enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_NKIND = 3 };

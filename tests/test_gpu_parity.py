@@ -220,6 +220,20 @@ def test_nb_sweep(nb):
     assert chkerr(n, ptr, row, val, x, b)[0] == 2
 
 
+@pytest.mark.parametrize("case", [SMALL[9], SMALL[11], SMALL[13], MEDIUM[1], MEDIUM[3]],
+                         ids=ids([SMALL[9], SMALL[11], SMALL[13], MEDIUM[1], MEDIUM[3]]))
+@pytest.mark.parametrize("tma", [0, 1])
+def test_large_tile_kernels_forced(case, tma, monkeypatch):
+    """Forces the 128 x 128 tile kernels (persistent TMA / cp.async variants) onto small problems so
+    ragged tiles, K tails and the scatter epilogue are all checked against the oracle."""
+    monkeypatch.setenv("SPLLT_B200_TILE_WAVE", "1")
+    monkeypatch.setenv("SPLLT_B200_TILE_L_MIN", "32")
+    if not tma:
+        monkeypatch.setenv("SPLLT_B200_NO_TMA", "1")
+    s, o, mat = both(case)
+    assert_factor_close(s.factor_entries(), o.factor_entries(), lower_mask(s))
+
+
 def test_full_size_properties_p3d64():
     """BASELINE config 2 (3D Poisson 64^3, nb = 512): too large for the oracle to finish in
     seconds, so parity is checked through size-independent properties: the acceptance gate,
