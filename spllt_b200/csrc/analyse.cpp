@@ -367,6 +367,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   const char* tw = getenv("SPLLT_B200_TILE_WAVE");
   const i64 tile_wave = tw ? atoll(tw) : 148;
   A.panel_tasks.clear();
+  A.npanel_groups = 0;
   A.tile_tasks.clear();
   A.launches.clear();
   A.tile_flops = 0;
@@ -480,15 +481,17 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
           pt.col0 = nd.sa + k0;
           pt.pad = 0;
           int r = k0 + pw;
-          bool first = true;
+          size_t g0 = A.panel_tasks.size();
+          pt.group = A.npanel_groups++;
           do {
             pt.r_off = nd.off + (i64)r * nd.ld + k0;
             pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
-            pt.first = first ? 1 : 0;
+            pt.store = 0;
             A.panel_tasks.push_back(pt);
-            first = false;
             r += TRSM_ROWS;
           } while (r < nd.m);
+          A.panel_tasks.back().store = 1;
+          for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
           // rest of this block column
           add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
         }

@@ -79,7 +79,7 @@ void Engine::upload_tables() {
   d_qrp = upload(S.q_rp);
   d_rowpos = upload(S.rowpos);
   CK(cudaMalloc(&d_info, sizeof(int)));
-  CK(cudaMalloc(&d_counters, std::max<size_t>(S.launches.size(), 1) * sizeof(int)));
+  CK(cudaMalloc(&d_counters, (S.launches.size() + S.npanel_groups + 1) * sizeof(int)));
   use_tma = (S.nb % 2 == 0) && !getenv("SPLLT_B200_NO_TMA");
   if (use_tma) {
     // one 2-D tensor map per supernode: the node's m x ld row-major matrix, box = 16 k x 128 rows,
@@ -138,7 +138,7 @@ void Engine::ensure_solve_buffers(int nrhs) {
 void Engine::launch_one(const Launch& L, cudaStream_t st) {
   DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
   switch (L.kind) {
-    case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, st); break;
+    case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, d_counters + A->launches.size(), st); break;
     case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
     case L_TILE_L:
       if (use_tma)   // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
@@ -156,7 +156,7 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
   if (phase <= 0) {
     CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
     CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
-    CK(cudaMemsetAsync(d_counters, 0, std::max<size_t>(S.launches.size(), 1) * sizeof(int), st));
+    CK(cudaMemsetAsync(d_counters, 0, (S.launches.size() + S.npanel_groups + 1) * sizeof(int), st));
     launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
     // several ranks add their contributions to the shared top: only rank 0 keeps A's entries there
     if (S.world > 1 && S.rank != 0 && S.arena > S.top_begin)
@@ -206,7 +206,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   CK(cudaEventRecord(ev[0], st));
   CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
   CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
-  CK(cudaMemsetAsync(d_counters, 0, std::max<size_t>(S.launches.size(), 1) * sizeof(int), st));
+  CK(cudaMemsetAsync(d_counters, 0, (S.launches.size() + S.npanel_groups + 1) * sizeof(int), st));
   launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
   CK(cudaEventRecord(ev[1], st));
   long long* dbg = nullptr;
@@ -218,7 +218,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
     if ((int)i == dbg_launch && L.kind == L_PANEL) {
       dbg_count = L.count;
       CK(cudaMalloc(&dbg, dbg_count * 8 * sizeof(long long)));
-      launch_panel_dbg(d_panel + L.begin, L.count, arena, d_info, dbg, st);
+      launch_panel_dbg(d_panel + L.begin, L.count, arena, d_info, d_counters + S.launches.size(), dbg, st);
     } else {
       launch_one(L, st);
     }
@@ -229,11 +229,10 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
     std::vector<long long> h(dbg_count * 8);
     CK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     for (i64 c = 0; c < std::min<i64>(dbg_count, 4); ++c)
-      fprintf(stderr, "panel dbg cta %lld (pw %d nrows %d): load_diag %lld potrf %lld load_rows %lld trsm %lld store %lld\n",
+      fprintf(stderr, "panel dbg cta %lld (pw %d nrows %d): load_diag %lld potrf %lld | solve_done@ %lld store %lld\n",
               (long long)c, S.panel_tasks[S.launches[dbg_launch].begin + c].pw,
               S.panel_tasks[S.launches[dbg_launch].begin + c].nrows, h[c * 8 + 1] - h[c * 8 + 0],
-              h[c * 8 + 2] - h[c * 8 + 1], h[c * 8 + 3] - h[c * 8 + 2], h[c * 8 + 4] - h[c * 8 + 3],
-              h[c * 8 + 5] - h[c * 8 + 4]);
+              h[c * 8 + 2] - h[c * 8 + 1], h[c * 8 + 3] - h[c * 8 + 1], h[c * 8 + 4] - h[c * 8 + 3]);
     CK(cudaFree(dbg));
   }
   float ms;

@@ -46,98 +46,177 @@ __global__ void k_assemble(double* __restrict__ arena, const i64* __restrict__ d
   for (; i < cnt; i += stride) arena[dst[i]] = val[src[i]];
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 // ------------------------------------------------------------------------------ panel
-// One inner panel: Cholesky of the pw x pw diagonal block + triangular solve of a chunk of rows.
-// Both phases work on 16-column register blocks with run-time outer loops: a fully unrolled
-// 64-column version is ~300 KB of straight-line SASS and runs instruction-fetch bound (measured
-// 67 us per panel); this form is a few thousand instructions.
-// Phase A: thread r owns row r of the diagonal block.  Per 16-column block: left-looking update
-// from the finished columns, then column by column (one barrier each, column published through
-// a double-buffered shared array): a_rj -= (a_rk / a_kk) * a_jk, so only rsqrt sits on the
-// per-column critical path; l_rk = a_rk * rsqrt(a_kk) is produced off it.
-// Phase B: thread r owns one row of the chunk: x_blk -= X_done * L^T (left-looking), then the
-// 16 x 16 diagonal solve.  Column c of L is contiguous in shared memory (Lt is L transposed).
+// One inner panel: Cholesky of the pw x pw diagonal block (a1) + triangular solve of a chunk of
+// rows against it (a2), pipelined inside the CTA.
+//   warp 0    : factorizes the diagonal block, 16 columns at a time; each lane owns rows l and
+//               l + 32 in registers.  Per 16-column block: left-looking update from the finished
+//               columns, then column by column (column published through a double-buffered
+//               shared array, __syncwarp only): a_rj -= (a_rk / a_kk) * a_jk, so only rsqrt sits
+//               on the per-column critical path; l_rk = a_rk * rsqrt(a_kk) is produced off it.
+//               After each block it arrives on that block's mbarrier.
+//   warps 1-4 : thread r owns one row of the chunk; as soon as block cb of L is published they
+//               run x_blk -= X_done * L^T (left-looking) and the 16 x 16 diagonal solve, i.e. the
+//               solve hides behind the factorization except for its last block.
+// Column c of L is contiguous in shared memory (Lt is L transposed).  Everything is written as
+// 16-wide register blocks with run-time outer loops: a fully unrolled 64-column version is
+// ~300 KB of straight-line SASS and runs instruction-fetch bound (measured 67 us per panel).
 constexpr int PLD = IB + 1;   // X rows: conflict-free when thread r reads X[r][c]
 constexpr int LTD = IB + 2;   // Lt rows: even, so (c*LTD + j) is 16-byte aligned for even j
 constexpr int PB = 16;        // register block
-constexpr int SMEM_PANEL = (IB * LTD + TRSM_ROWS * PLD + 2 * IB + IB) * 8;
+constexpr int PANEL_THREADS = 32 + TRSM_ROWS;
+constexpr int SMEM_PANEL = (IB * LTD + IB * PLD + TRSM_ROWS * PLD + 2 * IB + IB + 8) * 8;
 
 template <bool DBG>
-__global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
-                                                      int* __restrict__ info, long long* __restrict__ dbg) {
+__global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
+                                                          int* __restrict__ info, int* __restrict__ pcount,
+                                                          long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double sm[];
   double* Lt = sm;                        // [IB][LTD]   Lt[c][r] = L[r][c]
-  double* X = Lt + IB * LTD;              // [TRSM_ROWS][PLD]  (first holds the staged diagonal block)
+  double* S = Lt + IB * LTD;              // [IB][PLD]   staged diagonal block
+  double* X = S + IB * PLD;               // [TRSM_ROWS][PLD]
   double* col = X + TRSM_ROWS * PLD;      // [2][IB]
   double* dinv = col + 2 * IB;            // [IB]
+  unsigned long long* blk_done = reinterpret_cast<unsigned long long*>(dinv + IB);  // [4]
   const PanelTask t = tasks[blockIdx.x];
-  const int pw = t.pw, tid = threadIdx.x;
+  const int pw = t.pw, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* gd = arena + t.d_off;
   double* gr = arena + t.r_off;
-  // copies: lane -> column (<= 64), two rows per pass, no integer division, loads batched
-  const int cc = tid & (IB - 1), r2 = tid >> 6;
   if (DBG && tid == 0) dbg[blockIdx.x * 8 + 0] = clock64();
-  if (cc < pw) {
+  if (tid == 0) {
+    for (int i = 0; i < IB / PB; ++i) mbar_init(blk_done + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {  // diagonal block: lane -> column, no integer division, loads batched
+    const int cc = tid & (IB - 1), r2 = tid >> 6;
+    if (tid < 128 && cc < pw) {
 #pragma unroll 8
-    for (int r = r2; r < pw; r += 2) X[r * PLD + cc] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
+      for (int r = r2; r < pw; r += 2) S[r * PLD + cc] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
+    }
   }
   __syncthreads();
+  // every read of the un-factorized block by this CTA is complete: tell the storing CTA
+  if (tid == 0 && !t.store) {
+    __threadfence();
+    atomicAdd(pcount + t.group, 1);
+  }
   if (DBG && tid == 0) dbg[blockIdx.x * 8 + 1] = clock64();
-  const bool rowthread = tid < pw;
-  // ---------------- phase A
-  for (int c0 = 0; c0 < pw; c0 += PB) {
-    double a[PB];
+
+  if (warp == 0) {
+    // ---------------- factorization warp
+    const int r0 = lane, r1 = lane + 32;
+    for (int c0 = 0; c0 < pw; c0 += PB) {
+      double a0[PB], a1[PB];
 #pragma unroll
-    for (int j = 0; j < PB; ++j) a[j] = (rowthread && c0 + j < pw && c0 + j <= tid) ? X[tid * PLD + c0 + j] : 0.0;
-    if (rowthread && tid >= c0) {
+      for (int j = 0; j < PB; ++j) {
+        a0[j] = (r0 < pw && c0 + j < pw && c0 + j <= r0) ? S[r0 * PLD + c0 + j] : 0.0;
+        a1[j] = (r1 < pw && c0 + j < pw && c0 + j <= r1) ? S[r1 * PLD + c0 + j] : 0.0;
+      }
+      const bool u0 = r0 >= c0 && r0 < pw, u1 = r1 >= c0 && r1 < pw;
+#pragma unroll 4
       for (int c = 0; c < c0; ++c) {
-        double lrc = Lt[c * LTD + tid];
+        double l0 = u0 ? Lt[c * LTD + r0] : 0.0, l1 = u1 ? Lt[c * LTD + r1] : 0.0;
         const double2* lc = reinterpret_cast<const double2*>(Lt + c * LTD + c0);
 #pragma unroll
         for (int j = 0; j < PB / 2; ++j) {
           double2 l2 = lc[j];
-          a[2 * j] -= lrc * l2.x;
-          a[2 * j + 1] -= lrc * l2.y;
+          a0[2 * j] -= l0 * l2.x;
+          a0[2 * j + 1] -= l0 * l2.y;
+          a1[2 * j] -= l1 * l2.x;
+          a1[2 * j + 1] -= l1 * l2.y;
         }
       }
-    }
 #pragma unroll
-    for (int kk = 0; kk < PB; ++kk) {
-      const int k = c0 + kk;
-      if (k < pw) {
-        double* cb = col + (kk & 1) * IB;
-        if (rowthread && tid >= k) cb[tid] = a[kk];
-        __syncthreads();
-        if (rowthread && tid >= k) {
+      for (int kk = 0; kk < PB; ++kk) {
+        const int k = c0 + kk;
+        if (k < pw) {
+          double* cb = col + (kk & 1) * IB;
+          if (r0 >= k) cb[r0] = a0[kk];
+          if (r1 >= k) cb[r1] = a1[kk];
+          __syncwarp();
           double akk = cb[k];
-          if (tid == k && t.first && !(akk > 0.0)) atomicMin(info, t.col0 + k + 1);
-          double s = rsqrt(akk);
-          double me = a[kk];
-          Lt[k * LTD + tid] = me * s;
-          if (tid == k) dinv[k] = s;
-          double tt = me * (s * s);
+          // column entries needed below: issued before the rsqrt so their latency hides behind it
+          double cj[PB];
 #pragma unroll
-          for (int jj = kk + 1; jj < PB; ++jj)
-            if (c0 + jj <= tid) a[jj] -= tt * cb[c0 + jj];
+          for (int jj = kk + 1; jj < PB; ++jj) cj[jj] = cb[c0 + jj];
+          double s = rsqrt(akk), inv = s * s;
+          double t0 = a0[kk] * inv, t1 = a1[kk] * inv;
+          // entries above the diagonal (c0 + jj > row) receive garbage here; they are never
+          // published (all stores are guarded by row >= column), so no predication is needed
+#pragma unroll
+          for (int jj = kk + 1; jj < PB; ++jj) {
+            a0[jj] -= t0 * cj[jj];
+            a1[jj] -= t1 * cj[jj];
+          }
+          if (r0 >= k && r0 < pw) Lt[k * LTD + r0] = a0[kk] * s;
+          if (r1 >= k && r1 < pw) Lt[k * LTD + r1] = a1[kk] * s;
+          if (lane == 0) {
+            dinv[k] = s;
+            if (t.store && !(akk > 0.0)) atomicMin(info, t.col0 + k + 1);
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(blk_done + c0 / PB);
     }
-    __syncthreads();
+    if (DBG && lane == 0) dbg[blockIdx.x * 8 + 2] = clock64();
+    // store L_pp: only the CTA with the highest block index of the panel, and only once the
+    // other CTAs (all dispatched before this one) have read the original block
+    if (t.store) {
+      if (lane == 0 && t.ngroup > 1) {
+        volatile int* pc = pcount + t.group;
+        while (*pc < t.ngroup - 1) {
+        }
+        __threadfence();
+      }
+      __syncwarp();
+      for (int r = 0; r < pw; ++r)
+        for (int c = lane; c <= r; c += 32) gd[(i64)r * t.ld + c] = Lt[c * LTD + r];
+    }
+    return;
   }
-  // ---------------- phase B
-  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 2] = clock64();
-  if (cc < pw) {
+
+  // ---------------- solve warps
+  const int row = tid - 32;
+  {
+    const int cc = row & (IB - 1), r2 = row >> 6;
+    if (cc < pw) {
 #pragma unroll 8
-    for (int r = r2; r < t.nrows; r += 2) X[r * PLD + cc] = gr[(i64)r * t.ld + cc];
+      for (int r = r2; r < t.nrows; r += 2) X[r * PLD + cc] = gr[(i64)r * t.ld + cc];
+    }
   }
-  __syncthreads();
-  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 3] = clock64();
-  if (tid < t.nrows) {
-    double* xr = X + tid * PLD;
+  asm volatile("bar.sync 1, %0;" ::"n"(TRSM_ROWS) : "memory");
+  if (row < t.nrows) {
+    double* xr = X + row * PLD;
     for (int c0 = 0; c0 < pw; c0 += PB) {
       double x[PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) x[j] = (c0 + j < pw) ? xr[c0 + j] : 0.0;
+      mbar_wait(blk_done + c0 / PB, 0);
+#pragma unroll 4
       for (int c = 0; c < c0; ++c) {
         double xc = xr[c];
         const double2* lc = reinterpret_cast<const double2*>(Lt + c * LTD + c0);
@@ -163,18 +242,16 @@ __global__ void __launch_bounds__(TRSM_ROWS) k_panel(const PanelTask* __restrict
         if (c0 + j < pw) xr[c0 + j] = x[j];
     }
   }
-  __syncthreads();
-  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 4] = clock64();
-  if (cc < pw) {
+  asm volatile("bar.sync 1, %0;" ::"n"(TRSM_ROWS) : "memory");
+  if (DBG && row == 0) dbg[blockIdx.x * 8 + 3] = clock64();
+  {
+    const int cc = row & (IB - 1), r2 = row >> 6;
+    if (cc < pw) {
 #pragma unroll 8
-    for (int r = r2; r < t.nrows; r += 2) gr[(i64)r * t.ld + cc] = X[r * PLD + cc];
-    if (t.first) {
-#pragma unroll 8
-      for (int r = r2; r < pw; r += 2)
-        if (cc <= r) gd[(i64)r * t.ld + cc] = Lt[cc * LTD + r];
+      for (int r = r2; r < t.nrows; r += 2) gr[(i64)r * t.ld + cc] = X[r * PLD + cc];
     }
   }
-  if (DBG && tid == 0) dbg[blockIdx.x * 8 + 5] = clock64();
+  if (DBG && row == 0) dbg[blockIdx.x * 8 + 4] = clock64();
 }
 
 // ------------------------------------------------------------------------------ tile update
@@ -352,29 +429,6 @@ constexpr int TM_STAGE = 4 * TM_BOX;                     // A lo, A hi, B lo, B 
 constexpr int SMEM_TILE_TMA = TM_ST * TM_STAGE * 8 + 1024 + 256;
 static_assert(KC == 2 * TM_BOXK, "stage = two boxes per operand");
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "W_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra D_%=;\n"
-      "bra W_%=;\n"
-      "D_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 // 2-D tiled TMA load: box (c0 .. c0+16, c1 .. c1+128) of the tensor described by `tmap`
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
   asm volatile(
@@ -865,12 +919,13 @@ void launch_assemble(double* arena, const i64* dst, const i64* src, const double
   int blocks = (int)std::min<i64>((cnt + 255) / 256, 148 * 16);
   k_assemble<<<blocks, 256, 0, st>>>(arena, dst, src, val, cnt);
 }
-void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st) {
-  if (count > 0) k_panel<false><<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info, nullptr);
+void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, int* pcount, cudaStream_t st) {
+  if (count > 0) k_panel<false><<<(unsigned)count, PANEL_THREADS, SMEM_PANEL, st>>>(tasks, arena, info, pcount, nullptr);
 }
 // diagnostic: runs the panel kernel with clock64() stamps at its phase boundaries (8 per CTA)
-void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, long long* dbg, cudaStream_t st) {
-  if (count > 0) k_panel<true><<<(unsigned)count, TRSM_ROWS, SMEM_PANEL, st>>>(tasks, arena, info, dbg);
+void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, int* pcount, long long* dbg,
+                      cudaStream_t st) {
+  if (count > 0) k_panel<true><<<(unsigned)count, PANEL_THREADS, SMEM_PANEL, st>>>(tasks, arena, info, pcount, dbg);
 }
 void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
                       const void* tmaps, cudaStream_t st) {

@@ -16,8 +16,10 @@ struct DevMaps {          // inter-node update maps (device copies of Analysis::
 void kernels_init();      // opt-in shared memory sizes; call once per process
 void set_solve_maxw(int w);  // widest block column the solve kernels will see (shared memory size)
 void launch_assemble(double* arena, const i64* dst, const i64* src, const double* val, i64 cnt, cudaStream_t st);
-void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, cudaStream_t st);
-void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, long long* dbg, cudaStream_t st);
+// pcount: one counter per panel (PanelTask::group), zero at the start of a factorization
+void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, int* pcount, cudaStream_t st);
+void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, int* pcount, long long* dbg,
+                      cudaStream_t st);
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st);
 // persistent warp-specialised TMA variant of the 128 x 128 tiles; *counter must be 0 at launch
 void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,

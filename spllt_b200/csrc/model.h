@@ -52,13 +52,19 @@ struct HNode {
 // One inner panel of a block column (a1 + a2, src/spllt_kernels_mod.F90:1168-1189, :1217-1229):
 // every CTA factorizes the pw x pw diagonal block in shared memory (redundantly -- it is on
 // the critical path anyway and this saves a launch) and then solves its own chunk of rows,
-//   rows <- rows * L_pp^-T.   The CTA with `first` set also stores L_pp.
+//   rows <- rows * L_pp^-T.
+// L_pp is stored in place by exactly one CTA of the panel, the one with the highest block
+// index (`store`), and only after every other CTA of the panel has reported (through the
+// panel's counter) that it has finished reading the un-factorized block.
 struct PanelTask {
   i64 d_off;         // arena offset of the pw x pw diagonal block
   i64 r_off;         // first row of this chunk (below the diagonal block)
   int ld, pw, nrows;
   int col0;          // global pivot column of the panel's first column (error report)
-  int first, pad;
+  int store;         // 1: this CTA stores L_pp
+  int group;         // panel id (index of the panel's counter)
+  int ngroup;        // CTAs working on this panel
+  int pad;
 };
 // One dense tile update (a3 intra-node, a4 inter-node):
 //   C[i, j] -= sum_{k in [k0, k0+kk)} L[i, k] * L[j, k],  i in [i0,i0+mt), j in [j0,j0+nt), i >= j
@@ -139,6 +145,7 @@ struct Analysis {
 
   // factor schedule
   std::vector<PanelTask> panel_tasks;
+  int npanel_groups = 0;
   std::vector<TileTask> tile_tasks;
   std::vector<Launch> launches;
   std::vector<i64> q_base;         // per below-diagonal row: dest address when used as a COLUMN
