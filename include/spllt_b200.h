@@ -80,6 +80,9 @@ void spllt_b200_launch_breakdown(void *akeep, long long *out4);
  * one line per launch.  Synchronises. */
 void spllt_b200_profile_factor(void *fkeep, const double *d_val, double *ms4, const char *csv);
 
+/* same for one forward + backward solve: ms4 = {fwd_diag, fwd_upd, bwd_upd, bwd_diag} */
+void spllt_b200_profile_solve(void *fkeep, int nrhs, double *d_x, int ldx, double *ms4, const char *csv);
+
 /* ---- FP64 peak probes (no FP64 figure in MEASURED_PEAKS.json): enqueue a register-resident
  * DMMA (kind 0) or DFMA (kind 1) loop on every SM; returns the flops it will execute */
 double spllt_b200_peak_probe(int kind, int iters, void *stream);

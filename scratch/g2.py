@@ -43,6 +43,7 @@ def run(name, mat, nb, nrhs_list=(1,), reps=5):
         for d in dxs: s.solve_dev(d.data_ptr(), nrhs)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)/reps
+        print('  solve profile', {k: round(v,3) for k,v in s.profile_solve(dxs[0].data_ptr(), nrhs, 'gpurun_out/sprof_%s_%d.csv' % (name, nrhs)).items()})
         print('  nrhs %d solve %.3f ms  (%.1f GB/s of L traffic) bwd err %.2e ok %d launches %d' % (nrhs, ms, 2*8*s.num_factor/ms/1e6, err.max(), ok, L.spllt_b200_solve_launches(s.fkeep, 0)), flush=True)
     s.free()
 

@@ -106,6 +106,7 @@ def load_library(path=None):
         "spllt_b200_launch_breakdown": (None, [vp, llp]),
         "spllt_b200_profile_factor": (None, [vp, vp, dp, C.c_char_p]),
         "spllt_b200_node_owner": (C.c_int, [vp, C.c_int]),
+        "spllt_b200_profile_solve": (None, [vp, C.c_int, vp, C.c_int, dp, C.c_char_p]),
         "spllt_b200_peak_probe": (C.c_double, [C.c_int, C.c_int, vp]),
         "spllt_b200_arena_ptr": (vp, [vp]),
         "spllt_b200_partition": (None, [vp, vp, C.c_int, C.c_int]),
@@ -249,6 +250,12 @@ class SpLLT:
         self.L.spllt_b200_profile_factor(self.fkeep, C.c_void_p(d_val_ptr), _dp(ms),
                                          csv.encode() if csv else None)
         return dict(zip(("assemble", "panel", "tile_s", "tile_l"), ms.tolist()))
+
+    def profile_solve(self, d_x_ptr, nrhs, csv=None):
+        ms = np.zeros(4)
+        self.L.spllt_b200_profile_solve(self.fkeep, nrhs, C.c_void_p(d_x_ptr), self.n, _dp(ms),
+                                        csv.encode() if csv else None)
+        return dict(zip(("fwd_diag", "fwd_upd", "bwd_upd", "bwd_diag"), ms.tolist()))
 
     def pivot_flag(self):
         return self.L.spllt_b200_pivot_flag(self.fkeep)

@@ -512,6 +512,10 @@ void spllt_b200_profile_factor(void* fkeep, const double* d_val, double* ms4, co
   EE(fkeep)->profile_factor(d_val, ms4, csv);
 }
 
+void spllt_b200_profile_solve(void* fkeep, int nrhs, double* d_x, int ldx, double* ms4, const char* csv) {
+  EE(fkeep)->profile_solve(d_x, ldx, nrhs, ms4, csv);
+}
+
 double spllt_b200_peak_probe(int kind, int iters, void* stream) {
   require_gpu();
   if (kind >= 10) return launch_dmma_warps(iters, kind - 10, (cudaStream_t)stream);

@@ -265,10 +265,11 @@ void Engine::factor_host(const double* val) {
   factor(d_val);
 }
 
-void Engine::enqueue_solve(double* dx, int ldx, int nrhs, int job, cudaStream_t st) {
+// The sweeps work on the internal pivot-order vector d_xw only, so the captured graph does
+// not depend on the caller's x: the two permutation kernels are launched around it.
+void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
   const Analysis& S = *A;
   if (job == 0 || job == 1) {
-    launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
     for (int d = 0; d < S.ndepth; ++d) {
       const SolveLaunch& L = S.slaunch[d];
       launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
@@ -281,7 +282,6 @@ void Engine::enqueue_solve(double* dx, int ldx, int nrhs, int job, cudaStream_t 
       launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
       launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
     }
-    launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
   }
 }
 
@@ -289,19 +289,20 @@ void Engine::solve(double* dx, int ldx, int nrhs, int job) {
   upload_tables();
   if (A->n == 0 || nrhs <= 0) return;
   ensure_solve_buffers(nrhs);
-  SolveGraphKey key{dx, ldx, nrhs, job, stream, d_xw};
+  if (job == 0 || job == 1) launch_permute_in(dx, ldx, d_porder, d_xw, A->n, nrhs, stream);
   if (use_graph) {
+    SolveGraphKey key{nullptr, 0, nrhs, job, stream, d_xw};
     cudaGraphExec_t ex = nullptr;
     for (auto& e : solve_graphs)
       if (e.first == key) ex = e.second;
     if (!ex) {
       cudaGraph_t g;
       CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      enqueue_solve(dx, ldx, nrhs, job, stream);
+      enqueue_solve(nrhs, job, stream);
       CK(cudaStreamEndCapture(stream, &g));
       CK(cudaGraphInstantiate(&ex, g, 0));
       CK(cudaGraphDestroy(g));
-      if (solve_graphs.size() >= 8) {
+      if (solve_graphs.size() >= 16) {
         CK(cudaGraphExecDestroy(solve_graphs.front().second));
         solve_graphs.erase(solve_graphs.begin());
       }
@@ -309,8 +310,62 @@ void Engine::solve(double* dx, int ldx, int nrhs, int job) {
     }
     CK(cudaGraphLaunch(ex, stream));
   } else {
-    enqueue_solve(dx, ldx, nrhs, job, stream);
+    enqueue_solve(nrhs, job, stream);
   }
+  if (job == 0 || job == 2) launch_permute_out(dx, ldx, d_porder, d_xw, A->n, nrhs, stream);
+}
+
+// Un-graphed forward + backward solve with one event pair per launch: ms4 = {fwd_diag, fwd_upd,
+// bwd_upd, bwd_diag}; csv (optional) gets one line per launch.  Diagnostic only.
+void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms4, const char* csv) {
+  upload_tables();
+  for (int i = 0; i < 4; ++i) ms4[i] = 0;
+  if (A->n == 0) return;
+  ensure_solve_buffers(nrhs);
+  const Analysis& S = *A;
+  cudaStream_t st = stream;
+  std::vector<cudaEvent_t> ev(4 * S.ndepth + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
+  int e = 0;
+  CK(cudaEventRecord(ev[e++], st));
+  for (int d = 0; d < S.ndepth; ++d) {
+    const SolveLaunch& L = S.slaunch[d];
+    launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
+    CK(cudaEventRecord(ev[e++], st));
+    launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
+    CK(cudaEventRecord(ev[e++], st));
+  }
+  for (int d = S.ndepth - 1; d >= 0; --d) {
+    const SolveLaunch& L = S.slaunch[d];
+    launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
+    CK(cudaEventRecord(ev[e++], st));
+    launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
+    CK(cudaEventRecord(ev[e++], st));
+  }
+  launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
+  CK(cudaStreamSynchronize(st));
+  FILE* f = csv ? fopen(csv, "w") : nullptr;
+  if (f) fprintf(f, "kind,depth,ctas,ms\n");
+  for (int i = 0; i < 4 * S.ndepth; ++i) {
+    float ms;
+    CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    int kind, d;
+    if (i < 2 * S.ndepth) {
+      kind = i & 1;
+      d = i / 2;
+    } else {
+      int j = i - 2 * S.ndepth;
+      kind = 2 + (j & 1);
+      d = S.ndepth - 1 - j / 2;
+    }
+    ms4[kind] += ms;
+    const SolveLaunch& L = S.slaunch[d];
+    if (f)
+      fprintf(f, "%d,%d,%lld,%.6f\n", kind, d, (long long)((kind == 0 || kind == 3) ? L.diag_count : L.upd_count), ms);
+  }
+  if (f) fclose(f);
+  for (auto& x : ev) CK(cudaEventDestroy(x));
 }
 
 void Engine::solve_host(double* x, int nrhs, int job) {

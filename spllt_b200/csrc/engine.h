@@ -69,8 +69,9 @@ struct Engine {
   void factor_host(const double* val);
   void profile_factor(const double* dval, double* ms5, const char* csv);
   void launch_one(const Launch& L, cudaStream_t st);
-  void enqueue_solve(double* dx, int ldx, int nrhs, int job, cudaStream_t st);
+  void enqueue_solve(int nrhs, int job, cudaStream_t st);
   void solve(double* dx, int ldx, int nrhs, int job);
+  void profile_solve(double* dx, int ldx, int nrhs, double* ms4, const char* csv);
   void solve_host(double* x, int nrhs, int job);
   void sync();
   int pivot_flag();

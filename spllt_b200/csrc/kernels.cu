@@ -684,61 +684,86 @@ __global__ void k_permute_out(double* __restrict__ x, int ldx, const int* __rest
   x[porder[p] + (i64)r * ldx] = xw[i];
 }
 
-constexpr int SB = 32;        // sub-block of the in-CTA triangular solves
-constexpr int SBL = SB + 1;
+constexpr int SP = 64;         // panel width of the in-CTA triangular solves
+constexpr int SPL = SP + 1;
+constexpr int DIAG_THREADS = 512;
 
-// Forward: solve L_cc x = b for one block column (w x w lower triangle, row-major).
+// Forward: solve L_cc x = b for one block column (w x w lower triangle, row-major), 64 columns
+// at a time: (a) triangular solve of the 64 x 64 diagonal block -- one warp per right-hand side,
+// each lane owns rows l and l + 32, pivot broadcast by shuffle, reciprocals precomputed so the
+// per-column chain is multiply + shuffle + FMA; (b) the rows of the triangle below it:
+// warp-per-row dot products with coalesced 512-byte row segments, four rows in flight per warp.
 template <int RC>
-__global__ void __launch_bounds__(256) k_fwd_diag(const SolveBcol* __restrict__ bcs, const double* __restrict__ arena,
-                                                  double* __restrict__ xw, int nrhs) {
+__global__ void __launch_bounds__(DIAG_THREADS) k_fwd_diag(const SolveBcol* __restrict__ bcs,
+                                                           const double* __restrict__ arena, double* __restrict__ xw,
+                                                           int nrhs) {
   extern __shared__ double sm[];
   const SolveBcol b = bcs[blockIdx.x];
   const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
   double* xs = sm;                 // [RC][wp]
-  double* Ls = sm + RC * wp;       // [SB][SBL]
+  double* Ls = sm + RC * wp;       // [SP][SPL]
   const double* L = arena + b.off + (i64)b.r0 * b.ld + b.r0;
   double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
-  for (int idx = tid; idx < w * nr; idx += 256) {
-    int k = idx / nr, q = idx - k * nr;
-    xs[q * wp + k] = xg[(i64)k * nrhs + q];
+  for (int idx = tid; idx < w * RC; idx += DIAG_THREADS) {
+    int k = idx / RC, q = idx - k * RC;
+    xs[q * wp + k] = (q < nr) ? xg[(i64)k * nrhs + q] : 0.0;
   }
-  for (int jb = 0; jb < w; jb += SB) {
-    const int bs = min(SB, w - jb);
+  for (int p0 = 0; p0 < w; p0 += SP) {
+    const int pw = min(SP, w - p0);
     __syncthreads();
-    for (int idx = tid; idx < bs * SB; idx += 256) {
-      int i = idx >> 5, k = idx & 31;
-      Ls[i * SBL + k] = (k <= i) ? L[(i64)(jb + i) * b.ld + jb + k] : 0.0;
+    {
+      const int cc = tid & (SP - 1), rr = tid >> 6;
+#pragma unroll 8
+      for (int r = rr; r < pw; r += DIAG_THREADS / SP)
+        Ls[r * SPL + cc] = (cc <= r && cc < pw) ? L[(i64)(p0 + r) * b.ld + p0 + cc] : 0.0;
     }
     __syncthreads();
-    for (int q = warp; q < nr; q += 8) {
-      double xi = (lane < bs) ? xs[q * wp + jb + lane] : 0.0;
-      double rinv = (lane < bs) ? 1.0 / Ls[lane * SBL + lane] : 0.0;
-      for (int k = 0; k < bs; ++k) {
-        double xk = __shfl_sync(FULL, xi * rinv, k);
-        if (lane == k) xi = xk;
-        if (lane > k && lane < bs) xi -= Ls[lane * SBL + k] * xk;
+    for (int q = warp; q < nr; q += DIAG_THREADS / 32) {
+      const int i0 = lane, i1 = lane + 32;
+      double x0 = (i0 < pw) ? xs[q * wp + p0 + i0] : 0.0, x1 = (i1 < pw) ? xs[q * wp + p0 + i1] : 0.0;
+      const double d0 = (i0 < pw) ? 1.0 / Ls[i0 * SPL + i0] : 0.0, d1 = (i1 < pw) ? 1.0 / Ls[i1 * SPL + i1] : 0.0;
+      for (int k = 0; k < min(pw, 32); ++k) {
+        double xk = __shfl_sync(FULL, x0 * d0, k);
+        if (lane == k) x0 = xk;
+        if (i0 > k) x0 -= Ls[i0 * SPL + k] * xk;
+        x1 -= Ls[i1 * SPL + k] * xk;      // rows >= 32 are below every pivot < 32 (zero rows beyond pw)
       }
-      if (lane < bs) xs[q * wp + jb + lane] = xi;
+      for (int k = 32; k < pw; ++k) {
+        double xk = __shfl_sync(FULL, x1 * d1, k - 32);
+        if (lane == k - 32) x1 = xk;
+        if (i1 > k) x1 -= Ls[i1 * SPL + k] * xk;
+      }
+      if (i0 < pw) xs[q * wp + p0 + i0] = x0;
+      if (i1 < pw) xs[q * wp + p0 + i1] = x1;
     }
     __syncthreads();
-    for (int i = jb + bs + tid; i < w; i += 256) {
-      const double* lr = L + (i64)i * b.ld + jb;
-      double s[RC];
+    const int below = p0 + pw;
+    for (int ib = below + warp; ib < w; ib += 8 * (DIAG_THREADS / 32)) {
+      double l0[8], l1[8];
 #pragma unroll
-      for (int q = 0; q < RC; ++q) s[q] = 0.0;
-      for (int k = 0; k < bs; ++k) {
-        double l = lr[k];
-#pragma unroll
-        for (int q = 0; q < RC; ++q) s[q] += l * xs[q * wp + jb + k];
+      for (int u = 0; u < 8; ++u) {
+        int i = ib + u * (DIAG_THREADS / 32);
+        const double* lr = L + (i64)min(i, w - 1) * b.ld + p0;
+        l0[u] = (i < w && lane < pw) ? lr[lane] : 0.0;
+        l1[u] = (i < w && lane + 32 < pw) ? lr[lane + 32] : 0.0;
       }
 #pragma unroll
-      for (int q = 0; q < RC; ++q)
-        if (q < nr) xs[q * wp + i] -= s[q];
+      for (int u = 0; u < 8; ++u) {
+        int i = ib + u * (DIAG_THREADS / 32);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          double sacc = ((lane < pw) ? l0[u] * xs[q * wp + p0 + lane] : 0.0) +
+                        ((lane + 32 < pw) ? l1[u] * xs[q * wp + p0 + lane + 32] : 0.0);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
+          if (lane == 0 && i < w && q < nr) xs[q * wp + i] -= sacc;
+        }
+      }
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < w * nr; idx += 256) {
+  for (int idx = tid; idx < w * nr; idx += DIAG_THREADS) {
     int k = idx / nr, q = idx - k * nr;
     xg[(i64)k * nrhs + q] = xs[q * wp + k];
   }
@@ -766,6 +791,59 @@ __global__ void __launch_bounds__(256) k_fwd_upd(const SolveUpd* __restrict__ up
   const int rpw = 32 / g, sub = lane / g, lg = lane % g;
   const double* L = arena + b.off + (i64)u.r * b.ld + b.r0;
   const int* idx = index + b.idx_off + u.r;
+  if (g == 32) {
+    // wide block columns: two rows per warp in flight, 8 loads per row per lane issued together
+    for (int base = warp * 2; base < u.nrows; base += 16) {
+      const bool ok0 = base < u.nrows, ok1 = base + 1 < u.nrows;
+      const double* lr0 = L + (i64)base * b.ld;
+      const double* lr1 = L + (i64)min(base + 1, u.nrows - 1) * b.ld;
+      double s0[RC], s1[RC];
+#pragma unroll
+      for (int q = 0; q < RC; ++q) s0[q] = s1[q] = 0.0;
+      for (int kb = 0; kb < w; kb += 256) {
+        double v0[8], v1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int k = kb + j * 32 + lane;
+          v0[j] = (k < w && ok0) ? lr0[k] : 0.0;
+          v1[j] = (k < w && ok1) ? lr1[k] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int k = min(kb + j * 32 + lane, w - 1);
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            double xv = xs[q * wp + k];
+            s0[q] += v0[j] * xv;
+            s1[q] += v1[j] * xv;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          s0[q] += __shfl_xor_sync(FULL, s0[q], o);
+          s1[q] += __shfl_xor_sync(FULL, s1[q], o);
+        }
+      }
+      if (lane == 0) {
+        if (ok0) {
+          double* dst = xw + (i64)idx[base] * nrhs + rc0;
+#pragma unroll
+          for (int q = 0; q < RC; ++q)
+            if (q < nr) atomicAdd(dst + q, -s0[q]);
+        }
+        if (ok1) {
+          double* dst = xw + (i64)idx[base + 1] * nrhs + rc0;
+#pragma unroll
+          for (int q = 0; q < RC; ++q)
+            if (q < nr) atomicAdd(dst + q, -s1[q]);
+        }
+      }
+    }
+    return;
+  }
   for (int base = warp * rpw; base < u.nrows; base += 8 * rpw) {
     int row = base + sub;
     bool ok = row < u.nrows;
@@ -818,6 +896,7 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const SolveUpd* __restrict__ up
     double s[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) s[q] = 0.0;
+#pragma unroll 16
     for (int row = ty; row < u.nrows; row += ny) {
       double l = L[(i64)row * b.ld + k];
 #pragma unroll
@@ -829,58 +908,97 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const SolveUpd* __restrict__ up
   }
 }
 
-// Backward: solve L_cc^T x = b.
+// Backward: solve L_cc^T x = b, panels from last to first: (a) x_p -= L[below, p]^T x_below
+// (rows split over the warps, lanes over the panel's columns, cross-warp reduction in shared
+// memory), (b) transposed triangular solve of the diagonal block.
 template <int RC>
-__global__ void __launch_bounds__(256) k_bwd_diag(const SolveBcol* __restrict__ bcs, const double* __restrict__ arena,
-                                                  double* __restrict__ xw, int nrhs) {
+__global__ void __launch_bounds__(DIAG_THREADS) k_bwd_diag(const SolveBcol* __restrict__ bcs,
+                                                           const double* __restrict__ arena, double* __restrict__ xw,
+                                                           int nrhs) {
   extern __shared__ double sm[];
   const SolveBcol b = bcs[blockIdx.x];
   const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = DIAG_THREADS / 32;
   const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
-  double* xs = sm;
-  double* Ls = sm + RC * wp;
+  double* xs = sm;                    // [RC][wp]
+  double* Ls = sm + RC * wp;          // [SP][SPL]
+  double* red = Ls + SP * SPL;        // [NW][RC][SP]
   const double* L = arena + b.off + (i64)b.r0 * b.ld + b.r0;
   double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
-  for (int idx = tid; idx < w * nr; idx += 256) {
-    int k = idx / nr, q = idx - k * nr;
-    xs[q * wp + k] = xg[(i64)k * nrhs + q];
+  for (int idx = tid; idx < w * RC; idx += DIAG_THREADS) {
+    int k = idx / RC, q = idx - k * RC;
+    xs[q * wp + k] = (q < nr) ? xg[(i64)k * nrhs + q] : 0.0;
   }
-  const int nblk = (w + SB - 1) / SB;
-  for (int ib = nblk - 1; ib >= 0; --ib) {
-    const int jb = ib * SB, bs = min(SB, w - jb);
+  const int npan = (w + SP - 1) / SP;
+  for (int ip = npan - 1; ip >= 0; --ip) {
+    const int p0 = ip * SP, pw = min(SP, w - p0), below = p0 + pw;
     __syncthreads();
-    for (int idx = tid; idx < bs * SB; idx += 256) {
-      int i = idx >> 5, k = idx & 31;
-      Ls[i * SBL + k] = (k <= i) ? L[(i64)(jb + i) * b.ld + jb + k] : 0.0;
+    {
+      const int cc = tid & (SP - 1), rr = tid >> 6;
+#pragma unroll 8
+      for (int r = rr; r < pw; r += DIAG_THREADS / SP)
+        Ls[r * SPL + cc] = (cc <= r && cc < pw) ? L[(i64)(p0 + r) * b.ld + p0 + cc] : 0.0;
     }
-    __syncthreads();
-    for (int q = warp; q < nr; q += 8) {
-      double xi = (lane < bs) ? xs[q * wp + jb + lane] : 0.0;
-      double rinv = (lane < bs) ? 1.0 / Ls[lane * SBL + lane] : 0.0;
-      for (int k = bs - 1; k >= 0; --k) {
-        double xk = __shfl_sync(FULL, xi * rinv, k);
-        if (lane == k) xi = xk;
-        if (lane < k) xi -= Ls[k * SBL + lane] * xk;
-      }
-      if (lane < bs) xs[q * wp + jb + lane] = xi;
-    }
-    __syncthreads();
-    for (int i = tid; i < jb; i += 256) {
-      double s[RC];
+    // (a) partial column sums over this warp's rows
+    double a0[RC], a1[RC];
 #pragma unroll
-      for (int q = 0; q < RC; ++q) s[q] = 0.0;
-      for (int k = 0; k < bs; ++k) {
-        double l = L[(i64)(jb + k) * b.ld + i];
+    for (int q = 0; q < RC; ++q) a0[q] = a1[q] = 0.0;
+    for (int ib = below + warp; ib < w; ib += 8 * NW) {
+      double l0[8], l1[8];
 #pragma unroll
-        for (int q = 0; q < RC; ++q) s[q] += l * xs[q * wp + jb + k];
+      for (int u = 0; u < 8; ++u) {
+        int i = ib + u * NW;
+        const double* lr = L + (i64)min(i, w - 1) * b.ld + p0;
+        l0[u] = (i < w && lane < pw) ? lr[lane] : 0.0;
+        l1[u] = (i < w && lane + 32 < pw) ? lr[lane + 32] : 0.0;
       }
 #pragma unroll
-      for (int q = 0; q < RC; ++q)
-        if (q < nr) xs[q * wp + i] -= s[q];
+      for (int u = 0; u < 8; ++u) {
+        int i = min(ib + u * NW, w - 1);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          double xi = xs[q * wp + i];
+          a0[q] += l0[u] * xi;
+          a1[q] += l1[u] * xi;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RC; ++q) {
+      red[(warp * RC + q) * SP + lane] = a0[q];
+      red[(warp * RC + q) * SP + lane + 32] = a1[q];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RC * SP; idx += DIAG_THREADS) {
+      int q = idx / SP, k = idx - q * SP;
+      double ssum = 0.0;
+#pragma unroll
+      for (int u = 0; u < NW; ++u) ssum += red[(u * RC + q) * SP + k];
+      if (k < pw && q < nr) xs[q * wp + p0 + k] -= ssum;
+    }
+    __syncthreads();
+    // (b) transposed solve: x_k = x_k / L_kk, then x_i -= L[k][i] x_k for i < k
+    for (int q = warp; q < nr; q += NW) {
+      const int i0 = lane, i1 = lane + 32;
+      double x0 = (i0 < pw) ? xs[q * wp + p0 + i0] : 0.0, x1 = (i1 < pw) ? xs[q * wp + p0 + i1] : 0.0;
+      const double d0 = (i0 < pw) ? 1.0 / Ls[i0 * SPL + i0] : 0.0, d1 = (i1 < pw) ? 1.0 / Ls[i1 * SPL + i1] : 0.0;
+      for (int k = pw - 1; k >= 32; --k) {
+        double xk = __shfl_sync(FULL, x1 * d1, k - 32);
+        if (lane == k - 32) x1 = xk;
+        if (i1 < k) x1 -= Ls[k * SPL + i1] * xk;
+        x0 -= Ls[k * SPL + i0] * xk;
+      }
+      for (int k = min(pw, 32) - 1; k >= 0; --k) {
+        double xk = __shfl_sync(FULL, x0 * d0, k);
+        if (lane == k) x0 = xk;
+        if (i0 < k) x0 -= Ls[k * SPL + i0] * xk;
+      }
+      if (i0 < pw) xs[q * wp + p0 + i0] = x0;
+      if (i1 < pw) xs[q * wp + p0 + i1] = x1;
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < w * nr; idx += 256) {
+  for (int idx = tid; idx < w * nr; idx += DIAG_THREADS) {
     int k = idx / nr, q = idx - k * nr;
     xg[(i64)k * nrhs + q] = xs[q * wp + k];
   }
@@ -951,23 +1069,25 @@ void launch_permute_out(double* x, int ldx, const int* porder, const double* xw,
   if (tot > 0) k_permute_out<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, ldx, porder, xw, n, nrhs);
 }
 
-static inline int solve_smem(int maxw, int rc, bool tri) { return (rc * (maxw + 1) + (tri ? SB * SBL : 0)) * 8; }
+static inline int solve_smem(int maxw, int rc, bool tri) {
+  return (rc * (maxw + 1) + (tri ? SP * SPL + (DIAG_THREADS / 32) * rc * SP : 0)) * 8;
+}
 static int g_maxw = 1024;
 void set_solve_maxw(int w) { g_maxw = w; }
 
 void launch_fwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st) {
   if (count <= 0) return;
   if (nrhs == 1)
-    k_fwd_diag<1><<<dim3((unsigned)count, 1), 256, solve_smem(g_maxw, 1, true), st>>>(bc, arena, xw, nrhs);
+    k_fwd_diag<1><<<dim3((unsigned)count, 1), DIAG_THREADS, solve_smem(g_maxw, 1, true), st>>>(bc, arena, xw, nrhs);
   else
-    k_fwd_diag<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, solve_smem(g_maxw, 8, true), st>>>(bc, arena, xw, nrhs);
+    k_fwd_diag<8><<<dim3((unsigned)count, (nrhs + 7) / 8), DIAG_THREADS, solve_smem(g_maxw, 8, true), st>>>(bc, arena, xw, nrhs);
 }
 void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st) {
   if (count <= 0) return;
   if (nrhs == 1)
-    k_bwd_diag<1><<<dim3((unsigned)count, 1), 256, solve_smem(g_maxw, 1, true), st>>>(bc, arena, xw, nrhs);
+    k_bwd_diag<1><<<dim3((unsigned)count, 1), DIAG_THREADS, solve_smem(g_maxw, 1, true), st>>>(bc, arena, xw, nrhs);
   else
-    k_bwd_diag<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, solve_smem(g_maxw, 8, true), st>>>(bc, arena, xw, nrhs);
+    k_bwd_diag<8><<<dim3((unsigned)count, (nrhs + 7) / 8), DIAG_THREADS, solve_smem(g_maxw, 8, true), st>>>(bc, arena, xw, nrhs);
 }
 void launch_fwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
                     double* xw, int nrhs, cudaStream_t st) {

@@ -27,7 +27,7 @@ typedef int64_t i64;
 constexpr int IB = 64;      // inner panel width of the block-column factorization
 constexpr int LDPAD = 4;    // node leading dimension is a multiple of 4 doubles (32 B)
 constexpr int TRSM_ROWS = 128;  // rows per CTA of the panel solve
-constexpr int SOLVE_ROWS = 256; // rows per CTA of the solve update kernels
+constexpr int SOLVE_ROWS = 64;  // rows per CTA of the solve update kernels
 
 // ------------------------------------------------------------------ host symbolic tables
 struct HNode {
