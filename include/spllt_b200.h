@@ -94,6 +94,10 @@ void *spllt_b200_arena_ptr(void *fkeep);            /* device pointer of the HBM
  * above the split are "shared" (owner -1) and factorized by every rank after the reduction */
 void spllt_b200_partition(void *akeep, void *fkeep, int rank, int world);
 int spllt_b200_node_owner(void *akeep, int node);  /* node 1-based; -1 = shared top */
+/* host-only partition (no device state): used by the CPU multi-process tests */
+void spllt_b200_partition_host(void *akeep, int rank, int world);
+/* out[node] = number of inner panels (64 columns) this rank's schedule holds for each node */
+void spllt_b200_panel_coverage(void *akeep, long long *out);
 /* [begin, end) offsets (doubles) of the shared top-of-tree region in the arena */
 void spllt_b200_shared_region(void *akeep, long long *begin, long long *end);
 /* phase 0 = assemble + local subtrees, phase 1 = shared top; both asynchronous */

@@ -110,6 +110,8 @@ def load_library(path=None):
         "spllt_b200_peak_probe": (C.c_double, [C.c_int, C.c_int, vp]),
         "spllt_b200_arena_ptr": (vp, [vp]),
         "spllt_b200_partition": (None, [vp, vp, C.c_int, C.c_int]),
+        "spllt_b200_partition_host": (None, [vp, C.c_int, C.c_int]),
+        "spllt_b200_panel_coverage": (None, [vp, llp]),
         "spllt_b200_shared_region": (None, [vp, llp, llp]),
         "spllt_b200_factor_phase": (None, [vp, vp, vp, C.c_int]),
     }

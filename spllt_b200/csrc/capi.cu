@@ -539,6 +539,19 @@ void spllt_b200_partition(void* akeep, void* fkeep, int rank, int world) {
   build_factor_schedule(*A, env_int("SPLLT_B200_TILE_L_MIN", 128));
 }
 int spllt_b200_node_owner(void* akeep, int node) { return AA(akeep)->nodes[node - 1].owner; }
+// host-only variant of spllt_b200_partition (no device state touched): for CPU tests of the mapping
+void spllt_b200_partition_host(void* akeep, int rank, int world) {
+  Analysis* A = AA(akeep);
+  partition_tree(*A, rank, world);
+  build_factor_schedule(*A, env_int("SPLLT_B200_TILE_L_MIN", 128));
+}
+// out[node] = number of inner panels this rank's schedule holds for that node
+void spllt_b200_panel_coverage(void* akeep, long long* out) {
+  const Analysis& A = *AA(akeep);
+  for (int k = 0; k < A.nnodes; ++k) out[k] = 0;
+  for (const PanelTask& t : A.panel_tasks)
+    if (t.store) out[A.col2node[t.col0]]++;
+}
 void spllt_b200_factor_phase(void* akeep, void* fkeep, const double* d_val, int phase) {
   (void)akeep;
   Engine* e = EE(fkeep);

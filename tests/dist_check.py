@@ -1,0 +1,115 @@
+"""Multi-rank check, launched by torchrun (one rank per GPU; backend nccl) or, with
+SPLLT_DIST_CPU=1, on CPU with backend gloo (host logic only).
+
+GPU mode: every rank runs the distributed factorization (subtree mapping + all-reduce of the
+upper tree) and a plain single-GPU factorization of the same matrix, and compares the factor
+entries of every block column it holds (its own subtrees + the shared upper tree).
+CPU mode: the ranks exchange their partition tables over gloo and check that they agree, that
+every pruned subtree has exactly one owner and that the per-rank work lists cover every block
+column exactly once.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import spllt_b200 as sp  # noqa: E402
+from spllt_b200 import matrices as M  # noqa: E402
+from spllt_b200.dist import DistSpLLT  # noqa: E402
+
+
+def main():
+    cpu = os.environ.get("SPLLT_DIST_CPU", "0") == "1"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if cpu:
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grid = int(os.environ.get("SPLLT_DIST_GRID", "20"))
+    nb = int(os.environ.get("SPLLT_DIST_NB", "64"))
+    n, ptr, row, val = M.poisson3d(grid)
+    stream = None
+    if not cpu:
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+    d = DistSpLLT(nb=nb, rank=rank, world=world, stream=stream)
+    s = d.local
+    if cpu:
+        # host part of analyse + partition only (no device)
+        s.analyse(n, ptr, row)
+        s.L.spllt_b200_partition_host(s.akeep, rank, world)
+    else:
+        d.analyse(n, ptr, row)
+    nn = s.nnodes
+    own = np.array([s.L.spllt_b200_node_owner(s.akeep, k + 1) for k in range(nn)], dtype=np.int64)
+    small = s.small().astype(np.int64)
+    # ---- partition tables agree on all ranks
+    t = torch.from_numpy(own.copy())
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    if not cpu:
+        t = t.cuda()
+        gathered = [g.cuda() for g in gathered]
+    dist.all_gather(gathered, t)
+    for g in gathered:
+        assert torch.equal(g.cpu(), torch.from_numpy(own)), "ranks disagree on the subtree mapping"
+    assert np.all((own == -1) == (small == 0)), "upper tree must be shared, subtrees owned"
+    assert np.all((own >= 0) <= (own < world))
+    roots = np.nonzero(small == 1)[0]
+    for r in roots:   # whole subtree has the owner of its root
+        lo = int(s.nodes()[r, 4]) - 1
+        assert np.all(own[lo:r + 1] == own[r])
+    # ---- work lists: this rank's panels cover exactly its nodes + the shared ones
+    cnt = np.zeros(nn, dtype=np.int64)
+    s.L.spllt_b200_panel_coverage(s.akeep, cnt.ctypes.data_as(C.POINTER(C.c_longlong)))
+    mine = (own == rank) | (own == -1)
+    nodes = s.nodes()
+    npanels = np.array([sum(-(-min(nb, int(nodes[k, 1] - nodes[k, 0] + 1) - c0) // 64)
+                            for c0 in range(0, int(nodes[k, 1] - nodes[k, 0] + 1), nb)) for k in range(nn)])
+    assert np.array_equal(cnt[mine], npanels[mine]), "a block column of this rank is missing / duplicated"
+    assert np.all(cnt[~mine] == 0), "this rank schedules work on a foreign subtree"
+    if cpu:
+        dist.barrier()
+        if rank == 0:
+            print("dist_check cpu ok: world %d, %d nodes, %d subtrees" % (world, nn, len(roots)))
+        dist.destroy_process_group()
+        return
+
+    # ---- GPU: distributed factor vs single-GPU factor
+    d_val = torch.tensor(val, device="cuda")
+    d.factor_dev(d_val)
+    d.wait()
+    torch.cuda.synchronize()
+    assert d.pivot_flag() == 0
+    ref = sp.SpLLT(nb=nb, ncpu=world)
+    ref.analyse(n, ptr, row)
+    ref.factor(val)
+    ref.wait()
+    worst = 0.0
+    for k in range(nn):
+        if not mine[k]:
+            continue
+        ncol = int(nodes[k, 1] - nodes[k, 0] + 1)
+        bcol0 = int(s.blocks()[int(nodes[k, 6]) - 1, 7])
+        for c in range(-(-ncol // nb)):
+            a, b = s.lcol(bcol0 + c), ref.lcol(bcol0 + c)
+            w = min(nb, ncol - c * nb)
+            m = np.tril(np.ones((a.size // w, w), bool)).ravel()
+            worst = max(worst, float(np.abs(a - b)[m].max() / max(np.abs(b).max(), 1e-300)))
+    assert worst <= 1e-12, worst
+    t = torch.tensor([worst], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("dist_check gpu ok: world %d, max rel diff vs single-GPU factor %.2e; %s" % (world, t.item(), d.describe()))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
