@@ -328,19 +328,20 @@ struct Region {       // lower part of columns [jbeg, jend) x rows [max(j, ibeg_
   int jbeg, jend, ibeg_min, iend, k0, kk, src;
 };
 
-static i64 count_tiles(const Region& r, int T) {
+static i64 count_tiles(const Region& r, int T, int TN) {
   i64 c = 0;
-  for (int j0 = r.jbeg; j0 < r.jend; j0 += T) {
+  for (int j0 = r.jbeg; j0 < r.jend; j0 += TN) {
     int istart = std::max(j0, r.ibeg_min);
     if (r.iend > istart) c += (r.iend - istart + T - 1) / T;
   }
   return c;
 }
 
-static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r, int T) {
+// tiles of T rows x TN columns covering the lower part of the region
+static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r, int T, int TN) {
   const HNode& nd = *r.nd;
-  for (int j0 = r.jbeg; j0 < r.jend; j0 += T) {
-    int nt = std::min(T, r.jend - j0);
+  for (int j0 = r.jbeg; j0 < r.jend; j0 += TN) {
+    int nt = std::min(TN, r.jend - j0);
     int istart = std::max(j0, r.ibeg_min);
     for (int i0 = istart; i0 < r.iend; i0 += T) {
       TileTask t;
@@ -357,7 +358,7 @@ static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r,
       t.node = (int)(&nd - A.nodes.data());
       t.pad = 0;
       dst.push_back(t);
-      A.tile_flops += 2.0 * T * T * r.kk;
+      A.tile_flops += 2.0 * T * TN * r.kk;
     }
   }
 }
@@ -366,6 +367,11 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   const int nn = A.nnodes, nb = A.nb;
   const char* tw = getenv("SPLLT_B200_TILE_WAVE");
   const i64 tile_wave = tw ? atoll(tw) : 148;
+  {
+    const char* tn = getenv("SPLLT_B200_TILE_N");
+    const bool tma = (A.nb % 2 == 0) && !getenv("SPLLT_B200_NO_TMA");
+    A.tile_n = (tma && !(tn && atoi(tn) == 128)) ? 64 : 128;
+  }
   A.panel_tasks.clear();
   A.npanel_groups = 0;
   A.tile_tasks.clear();
@@ -425,12 +431,12 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     for (size_t i = 0; i < regions.size(); ++i) {
       const Region& r = regions[i];
       big[i] = (r.jend - r.jbeg) >= tile_l_min && (r.iend - r.jbeg) >= tile_l_min && r.kk >= 16;
-      if (big[i]) nlarge += count_tiles(r, 128);
+      if (big[i]) nlarge += count_tiles(r, 128, 128);
     }
     const bool use_large = nlarge >= tile_wave;
     for (size_t i = 0; i < regions.size(); ++i) {
-      if (use_large && big[i]) emit_tiles(A, tl, regions[i], 128);
-      else emit_tiles(A, ts, regions[i], 64);
+      if (use_large && big[i]) emit_tiles(A, tl, regions[i], 128, A.tile_n);
+      else emit_tiles(A, ts, regions[i], 64, 64);
     }
     regions.clear();
     auto work = [](const TileTask& t) { return (i64)t.kk * t.mt * t.nt; };
@@ -448,72 +454,83 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     }
   };
 
+  // Time slots at PANEL granularity (as-soon-as-possible): a node's first panel runs in the slot
+  // after its last child's last panel, and its panels occupy consecutive slots.  The number of
+  // slots is the true critical path of the tree in panel steps (162 for 3-D Poisson 64^3,
+  // nb = 512) instead of the sum over block-column levels of the widest block column (253).
+  // One slot = one panel launch + one tile launch group holding, for every node active in the
+  // slot: the inner update of its block column, or (last panel of a block column) the outer
+  // update of the node's later block columns, and (last panel of the node) its inter-node
+  // updates -- the latency-bound inner updates ride along with the throughput-bound ones.
+  struct Step { int node, c, p; };
+  std::vector<int> nsteps(nn, 0);
+  for (int s = 0; s < nn; ++s)
+    for (int c = 0; c < A.nodes[s].nc; ++c) nsteps[s] += cdiv(std::min(nb, A.nodes[s].n - c * nb), IB);
   for (int phase = 0; phase < 2; ++phase) {
     cur_phase = phase;
-    std::vector<std::vector<int>> at(A.ndepth);  // global block-column ids per depth
-    for (int s = 0; s < nn; ++s) {
+    auto mine = [&](int s) {
       int own = A.nodes[s].owner;
-      bool mine = (A.world <= 1) ? (phase == 0) : (phase == 0 ? own == A.rank : own < 0);
-      if (!mine) continue;
-      for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
+      return (A.world <= 1) ? (phase == 0) : (phase == 0 ? own == A.rank : own < 0);
+    };
+    std::vector<int> t0(nn, 0);
+    int nslots = 0;
+    for (int s = 0; s < nn; ++s) {
+      if (!mine(s)) continue;
+      int tend = t0[s] + nsteps[s];
+      nslots = std::max(nslots, tend);
+      int par = A.nodes[s].parent;
+      if (par >= 0 && mine(par)) t0[par] = std::max(t0[par], tend);
     }
-    for (int d = 0; d < A.ndepth; ++d) {
+    std::vector<std::vector<Step>> at(nslots);
+    for (int s = 0; s < nn; ++s) {
+      if (!mine(s)) continue;
+      int t = t0[s];
+      for (int c = 0; c < A.nodes[s].nc; ++c) {
+        int w = std::min(nb, A.nodes[s].n - c * nb);
+        for (int p = 0; p * IB < w; ++p) at[t++].push_back({s, c, p});
+      }
+    }
+    for (int d = 0; d < nslots; ++d) {
       if (at[d].empty()) continue;
-      int maxsteps = 0;
-      for (int g : at[d]) {
-        const HNode& nd = A.nodes[A.bcol_node[g]];
-        int w = std::min(nb, nd.n - A.bcol_c[g] * nb);
-        maxsteps = std::max(maxsteps, cdiv(w, IB));
-      }
-      for (int p = 0; p < maxsteps; ++p) {
-        i64 p0 = A.panel_tasks.size();
-        for (int g : at[d]) {
-          const HNode& nd = A.nodes[A.bcol_node[g]];
-          int r0 = A.bcol_c[g] * nb;
-          int w = std::min(nb, nd.n - r0);
-          if (p * IB >= w) continue;
-          int pw = std::min(IB, w - p * IB);
-          int k0 = r0 + p * IB;
-          PanelTask pt;
-          pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
-          pt.ld = nd.ld;
-          pt.pw = pw;
-          pt.col0 = nd.sa + k0;
-          pt.pad = 0;
-          int r = k0 + pw;
-          size_t g0 = A.panel_tasks.size();
-          pt.group = A.npanel_groups++;
-          do {
-            pt.r_off = nd.off + (i64)r * nd.ld + k0;
-            pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
-            pt.store = 0;
-            A.panel_tasks.push_back(pt);
-            r += TRSM_ROWS;
-          } while (r < nd.m);
-          A.panel_tasks.back().store = 1;
-          for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
-          // rest of this block column
-          add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
-        }
-        if ((i64)A.panel_tasks.size() > p0)
-          A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0});
-        flush_tiles(d, 1);
-      }
-      // outer updates of the block columns finished at this depth
-      for (int g : at[d]) {
-        const HNode& nd = A.nodes[A.bcol_node[g]];
-        int c = A.bcol_c[g];
-        int r0 = c * nb;
+      i64 p0 = A.panel_tasks.size();
+      for (const Step& st : at[d]) {
+        const HNode& nd = A.nodes[st.node];
+        int r0 = st.c * nb;
         int w = std::min(nb, nd.n - r0);
-        if (c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
+        int pw = std::min(IB, w - st.p * IB);
+        int k0 = r0 + st.p * IB;
+        PanelTask pt;
+        pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
+        pt.ld = nd.ld;
+        pt.pw = pw;
+        pt.col0 = nd.sa + k0;
+        pt.pad = 0;
+        int r = k0 + pw;
+        size_t g0 = A.panel_tasks.size();
+        pt.group = A.npanel_groups++;
+        do {
+          pt.r_off = nd.off + (i64)r * nd.ld + k0;
+          pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
+          pt.store = 0;
+          A.panel_tasks.push_back(pt);
+          r += TRSM_ROWS;
+        } while (r < nd.m);
+        A.panel_tasks.back().store = 1;
+        for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
+        const bool last_in_bcol = k0 + pw >= r0 + w;
+        if (!last_in_bcol) {
+          // a3 inside the block column: the columns right of this panel (K = pw)
+          add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+        } else {
+          // a3: the finished block column updates the node's later block columns (K = w)
+          if (st.c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
+          // a4: the finished node updates its ancestors (K = n)
+          if (st.c + 1 == nd.nc && nd.m > nd.n)
+            add_tiles(A, ts, tl, nd, nd.n, nd.m, 0, nd.m, 0, nd.n, st.node, tile_l_min);
+        }
       }
-      flush_tiles(d, 2);
-      for (int g : at[d]) {
-        const HNode& nd = A.nodes[A.bcol_node[g]];
-        if (A.bcol_c[g] + 1 == nd.nc && nd.m > nd.n)
-          add_tiles(A, ts, tl, nd, nd.n, nd.m, 0, nd.m, 0, nd.n, A.bcol_node[g], tile_l_min);
-      }
-      flush_tiles(d, 3);
+      A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0});
+      flush_tiles(d, 4);
     }
   }
 }

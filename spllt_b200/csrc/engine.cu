@@ -58,6 +58,12 @@ void Engine::upload_tables() {
     own_stream = true;
   }
   if (!stream) stream = own;
+  if (!side) {
+    CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  overlap_tiles = !getenv("SPLLT_B200_NO_OVERLAP");
   CK(cudaMalloc(&arena, std::max<i64>(S.arena, 1) * sizeof(double)));
   CK(cudaMemset(arena, 0, std::max<i64>(S.arena, 1) * sizeof(double)));
   // A -> L map with arena addresses
@@ -97,23 +103,26 @@ void Engine::upload_tables() {
     }
     encode_t encode = (encode_t)fn;
     std::vector<CUtensorMap> maps(std::max(S.nnodes, 1));
-    for (int k = 0; k < S.nnodes; ++k) {
-      const HNode& nd = S.nodes[k];
-      cuuint64_t dims[2] = {(cuuint64_t)nd.ld, (cuuint64_t)nd.m};
-      cuuint64_t strides[1] = {(cuuint64_t)nd.ld * 8};
-      cuuint32_t box[2] = {16, 128};
-      cuuint32_t es[2] = {1, 1};
-      CUresult r = encode(&maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, arena + nd.off, dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) {
-        fprintf(stderr, "spllt_b200: cuTensorMapEncodeTiled failed (%d) for node %d (m=%d ld=%d)\n", (int)r, k, nd.m,
-                nd.ld);
-        abort();
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0: 128-row boxes (A operand), pass 1: tile_n-row boxes (B operand)
+      for (int k = 0; k < S.nnodes; ++k) {
+        const HNode& nd = S.nodes[k];
+        cuuint64_t dims[2] = {(cuuint64_t)nd.ld, (cuuint64_t)nd.m};
+        cuuint64_t strides[1] = {(cuuint64_t)nd.ld * 8};
+        cuuint32_t box[2] = {16, (cuuint32_t)(pass == 0 ? 128 : S.tile_n)};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(&maps[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, arena + nd.off, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+          fprintf(stderr, "spllt_b200: cuTensorMapEncodeTiled failed (%d) for node %d (m=%d ld=%d)\n", (int)r, k, nd.m,
+                  nd.ld);
+          abort();
+        }
       }
+      void** dst = pass == 0 ? &d_tmaps : &d_tmaps_b;
+      CK(cudaMalloc(dst, maps.size() * sizeof(CUtensorMap)));
+      CK(cudaMemcpy(*dst, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     }
-    CK(cudaMalloc(&d_tmaps, maps.size() * sizeof(CUtensorMap)));
-    CK(cudaMemcpy(d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   }
   d_sb = upload(S.sbcols);
   d_su = upload(S.supds);
@@ -142,7 +151,8 @@ void Engine::launch_one(const Launch& L, cudaStream_t st) {
     case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
     case L_TILE_L:
       if (use_tma)   // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
-        launch_tiles_tma(d_tile + L.begin, L.count, d_counters + (&L - A->launches.data()), arena, mp, d_tmaps, st);
+        launch_tiles_tma(d_tile + L.begin, L.count, d_counters + (&L - A->launches.data()), arena, mp, d_tmaps,
+                         d_tmaps_b, A->tile_n, st);
       else
         launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st);
       break;
@@ -162,8 +172,24 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     if (S.world > 1 && S.rank != 0 && S.arena > S.top_begin)
       CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
   }
-  for (const Launch& L : S.launches) {
+  // The small-tile and large-tile launches of one slot write disjoint destinations (or use
+  // atomics): fork them onto two streams so the latency-bound small launch overlaps the
+  // throughput-bound one.  (Works inside stream capture: the side stream joins the graph.)
+  const bool fork = overlap_tiles && side != nullptr;
+  for (size_t i = 0; i < S.launches.size(); ++i) {
+    const Launch& L = S.launches[i];
     if (phase >= 0 && L.phase != phase) continue;
+    if (fork && L.kind == L_TILE_S && i + 1 < S.launches.size() && S.launches[i + 1].kind == L_TILE_L &&
+        S.launches[i + 1].depth == L.depth && S.launches[i + 1].phase == L.phase) {
+      CK(cudaEventRecord(ev_fork, st));
+      CK(cudaStreamWaitEvent(side, ev_fork, 0));
+      launch_one(L, side);
+      launch_one(S.launches[i + 1], st);
+      CK(cudaEventRecord(ev_join, side));
+      CK(cudaStreamWaitEvent(st, ev_join, 0));
+      ++i;
+      continue;
+    }
     launch_one(L, st);
   }
 }
@@ -247,8 +273,8 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
     if (f) {
       double fl = 0;
       if (L.kind != L_PANEL) {
-        double T = L.kind == L_TILE_L ? 128.0 : 64.0;
-        for (i64 k = L.begin; k < L.begin + L.count; ++k) fl += 2.0 * T * T * S.tile_tasks[k].kk;
+        double T = L.kind == L_TILE_L ? 128.0 : 64.0, TN = L.kind == L_TILE_L ? (double)S.tile_n : 64.0;
+        for (i64 k = L.begin; k < L.begin + L.count; ++k) fl += 2.0 * T * TN * S.tile_tasks[k].kk;
       }
       fprintf(f, "%zu,%d,%d,%d,%lld,%.6f,%.0f\n", i, L.kind, L.tag, L.depth, (long long)L.count, ms, fl);
     }
@@ -427,14 +453,24 @@ void Engine::release() {
   cudaFree(d_info);
   cudaFree(d_counters);
   if (d_tmaps) cudaFree(d_tmaps);
-  d_tmaps = nullptr;
+  if (d_tmaps_b) cudaFree(d_tmaps_b);
+  d_tmaps = d_tmaps_b = nullptr;
   cudaFree(d_sb);
   cudaFree(d_su);
   cudaFree(d_index);
   cudaFree(d_porder);
   if (d_xw) cudaFree(d_xw);
   if (d_x) cudaFree(d_x);
+  if (stream == own) stream = nullptr;
   if (own_stream) cudaStreamDestroy(own);
+  own_stream = false;
+  own = nullptr;
+  if (side) {
+    cudaStreamDestroy(side);
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+    side = nullptr;
+  }
   uploaded = false;
 }
 

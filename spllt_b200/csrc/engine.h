@@ -29,6 +29,9 @@ struct Engine {
   bool uploaded = false, factored = false, use_graph = true;
   cudaStream_t stream = nullptr, own = nullptr;
   bool own_stream = false;
+  cudaStream_t side = nullptr;  // second stream: small-tile launches overlap the large-tile launch of their slot
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_tiles = true;
   int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
 
   double* arena = nullptr;
@@ -44,7 +47,8 @@ struct Engine {
   int* d_info = nullptr;
   int* d_counters = nullptr;  // one tile counter per launch (persistent TMA tile kernel)
   bool use_tma = true;
-  void* d_tmaps = nullptr;    // CUtensorMap[nnodes] in device memory (128 bytes each)
+  void* d_tmaps = nullptr;    // CUtensorMap[nnodes] in device memory (128 bytes each), 128-row boxes
+  void* d_tmaps_b = nullptr;  // same with tile_n-row boxes (B operand)
   SolveBcol* d_sb = nullptr;
   SolveUpd* d_su = nullptr;
   int* d_index = nullptr;

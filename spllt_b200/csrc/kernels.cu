@@ -69,6 +69,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+// same, with back-off: used by warps that wait for a long time next to latency-critical warps
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done) __nanosleep(200);
+  }
+}
 // ------------------------------------------------------------------------------ panel
 // One inner panel: Cholesky of the pw x pw diagonal block (a1) + triangular solve of a chunk of
 // rows against it (a2), pipelined inside the CTA.
@@ -87,7 +103,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 constexpr int PLD = IB + 1;   // X rows: conflict-free when thread r reads X[r][c]
 constexpr int LTD = IB + 2;   // Lt rows: even, so (c*LTD + j) is 16-byte aligned for even j
 constexpr int PB = 16;        // register block
-constexpr int PANEL_THREADS = 32 + TRSM_ROWS;
+constexpr int PANEL_THREADS = 128 + TRSM_ROWS;
 constexpr int SMEM_PANEL = (IB * LTD + IB * PLD + TRSM_ROWS * PLD + 2 * IB + IB + 8) * 8;
 
 template <bool DBG>
@@ -107,14 +123,14 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
   double* gr = arena + t.r_off;
   if (DBG && tid == 0) dbg[blockIdx.x * 8 + 0] = clock64();
   if (tid == 0) {
-    for (int i = 0; i < IB / PB; ++i) mbar_init(blk_done + i, 1);
+    for (int i = 0; i < IB / PB; ++i) mbar_init(blk_done + i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {  // diagonal block: lane -> column, no integer division, loads batched
     const int cc = tid & (IB - 1), r2 = tid >> 6;
-    if (tid < 128 && cc < pw) {
+    if (cc < pw) {
 #pragma unroll 8
-      for (int r = r2; r < pw; r += 2) S[r * PLD + cc] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
+      for (int r = r2; r < pw; r += 4) S[r * PLD + cc] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
     }
   }
   __syncthreads();
@@ -125,28 +141,28 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
   }
   if (DBG && tid == 0) dbg[blockIdx.x * 8 + 1] = clock64();
 
-  if (warp == 0) {
-    // ---------------- factorization warp
-    const int r0 = lane, r1 = lane + 32;
+  if (tid < 128) {
+    // ---------------- factorization warps (4): thread (r, h) owns row r, columns h*8 .. h*8+7 of
+    // the current 16-column block.  A lone warp issues one DFMA per ~4 cycles, so the block
+    // updates are spread over the four SM sub-partitions; columns are exchanged through a
+    // double-buffered shared array with one 128-thread named barrier per column.
+    const int r = tid & 63, h = tid >> 6;
     for (int c0 = 0; c0 < pw; c0 += PB) {
-      double a0[PB], a1[PB];
+      const int cbase = c0 + h * 8;
+      double a[8];
 #pragma unroll
-      for (int j = 0; j < PB; ++j) {
-        a0[j] = (r0 < pw && c0 + j < pw && c0 + j <= r0) ? S[r0 * PLD + c0 + j] : 0.0;
-        a1[j] = (r1 < pw && c0 + j < pw && c0 + j <= r1) ? S[r1 * PLD + c0 + j] : 0.0;
-      }
-      const bool u0 = r0 >= c0 && r0 < pw, u1 = r1 >= c0 && r1 < pw;
+      for (int j = 0; j < 8; ++j) a[j] = (r < pw && cbase + j < pw && cbase + j <= r) ? S[r * PLD + cbase + j] : 0.0;
+      if (r >= c0 && r < pw) {
 #pragma unroll 4
-      for (int c = 0; c < c0; ++c) {
-        double l0 = u0 ? Lt[c * LTD + r0] : 0.0, l1 = u1 ? Lt[c * LTD + r1] : 0.0;
-        const double2* lc = reinterpret_cast<const double2*>(Lt + c * LTD + c0);
+        for (int c = 0; c < c0; ++c) {
+          double lrc = Lt[c * LTD + r];
+          const double2* lc = reinterpret_cast<const double2*>(Lt + c * LTD + cbase);
 #pragma unroll
-        for (int j = 0; j < PB / 2; ++j) {
-          double2 l2 = lc[j];
-          a0[2 * j] -= l0 * l2.x;
-          a0[2 * j + 1] -= l0 * l2.y;
-          a1[2 * j] -= l1 * l2.x;
-          a1[2 * j + 1] -= l1 * l2.y;
+          for (int j = 0; j < 4; ++j) {
+            double2 l2 = lc[j];
+            a[2 * j] -= lrc * l2.x;
+            a[2 * j + 1] -= lrc * l2.y;
+          }
         }
       }
 #pragma unroll
@@ -154,53 +170,57 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
         const int k = c0 + kk;
         if (k < pw) {
           double* cb = col + (kk & 1) * IB;
-          if (r0 >= k) cb[r0] = a0[kk];
-          if (r1 >= k) cb[r1] = a1[kk];
-          __syncwarp();
-          double akk = cb[k];
-          // column entries needed below: issued before the rsqrt so their latency hides behind it
-          double cj[PB];
+          const int hh = kk >> 3;
+          if (h == hh && r >= k) cb[r] = a[kk & 7];
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (h >= hh) {
+            double akk = cb[k];
+            double me = cb[r];
+            double cj[8];
 #pragma unroll
-          for (int jj = kk + 1; jj < PB; ++jj) cj[jj] = cb[c0 + jj];
-          double s = rsqrt(akk), inv = s * s;
-          double t0 = a0[kk] * inv, t1 = a1[kk] * inv;
-          // entries above the diagonal (c0 + jj > row) receive garbage here; they are never
-          // published (all stores are guarded by row >= column), so no predication is needed
+            for (int j = 0; j < 8; ++j) cj[j] = cb[cbase + j];
+            double s = rsqrt(akk);
+            double tt = me * (s * s);
+            // columns <= k of this thread (only when h == hh) receive garbage: they are final
+            // and already published; entries above the diagonal are never stored
 #pragma unroll
-          for (int jj = kk + 1; jj < PB; ++jj) {
-            a0[jj] -= t0 * cj[jj];
-            a1[jj] -= t1 * cj[jj];
-          }
-          if (r0 >= k && r0 < pw) Lt[k * LTD + r0] = a0[kk] * s;
-          if (r1 >= k && r1 < pw) Lt[k * LTD + r1] = a1[kk] * s;
-          if (lane == 0) {
-            dinv[k] = s;
-            if (t.store && !(akk > 0.0)) atomicMin(info, t.col0 + k + 1);
+            for (int j = 0; j < 8; ++j) a[j] -= tt * cj[j];
+            if (h == hh) {
+              if (r >= k && r < pw) Lt[k * LTD + r] = me * s;
+              if (r == k) {
+                dinv[k] = s;
+                if (t.store && !(akk > 0.0)) atomicMin(info, t.col0 + k + 1);
+              }
+            }
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(blk_done + c0 / PB);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if ((tid & 31) == 0) mbar_arrive(blk_done + c0 / PB);
     }
-    if (DBG && lane == 0) dbg[blockIdx.x * 8 + 2] = clock64();
+    if (DBG && tid == 0) dbg[blockIdx.x * 8 + 2] = clock64();
     // store L_pp: only the CTA with the highest block index of the panel, and only once the
     // other CTAs (all dispatched before this one) have read the original block
     if (t.store) {
-      if (lane == 0 && t.ngroup > 1) {
+      if (tid == 0 && t.ngroup > 1) {
         volatile int* pc = pcount + t.group;
         while (*pc < t.ngroup - 1) {
         }
         __threadfence();
       }
-      __syncwarp();
-      for (int r = 0; r < pw; ++r)
-        for (int c = lane; c <= r; c += 32) gd[(i64)r * t.ld + c] = Lt[c * LTD + r];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int cc = tid & 63, r2 = tid >> 6;
+      if (cc < pw) {
+#pragma unroll 8
+        for (int rr = r2; rr < pw; rr += 2)
+          if (cc <= rr) gd[(i64)rr * t.ld + cc] = Lt[cc * LTD + rr];
+      }
     }
     return;
   }
 
   // ---------------- solve warps
-  const int row = tid - 32;
+  const int row = tid - 128;
   {
     const int cc = row & (IB - 1), r2 = row >> 6;
     if (cc < pw) {
@@ -208,14 +228,14 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
       for (int r = r2; r < t.nrows; r += 2) X[r * PLD + cc] = gr[(i64)r * t.ld + cc];
     }
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(TRSM_ROWS) : "memory");
+  asm volatile("bar.sync 2, %0;" ::"n"(TRSM_ROWS) : "memory");
   if (row < t.nrows) {
     double* xr = X + row * PLD;
     for (int c0 = 0; c0 < pw; c0 += PB) {
       double x[PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) x[j] = (c0 + j < pw) ? xr[c0 + j] : 0.0;
-      mbar_wait(blk_done + c0 / PB, 0);
+      mbar_wait_backoff(blk_done + c0 / PB, 0);
 #pragma unroll 4
       for (int c = 0; c < c0; ++c) {
         double xc = xr[c];
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
         if (c0 + j < pw) xr[c0 + j] = x[j];
     }
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(TRSM_ROWS) : "memory");
+  asm volatile("bar.sync 2, %0;" ::"n"(TRSM_ROWS) : "memory");
   if (DBG && row == 0) dbg[blockIdx.x * 8 + 3] = clock64();
   {
     const int cc = row & (IB - 1), r2 = row >> 6;
@@ -422,11 +442,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 // The 128B swizzle XORs the 16-byte chunk index with (row % 8); fragment row rho of an 8-row
 // group is read from shared row sigma(rho) = {0,2,4,6,1,3,5,7}, which makes the 8-byte fragment
 // loads of a half-warp hit 16 distinct bank pairs.
-constexpr int TM_ST = 3;
 constexpr int TM_BOXK = 16;                              // doubles per box row (128 bytes)
-constexpr int TM_BOX = 128 * TM_BOXK;                    // doubles per box (16 KB)
-constexpr int TM_STAGE = 4 * TM_BOX;                     // A lo, A hi, B lo, B hi  (KC = 32)
-constexpr int SMEM_TILE_TMA = TM_ST * TM_STAGE * 8 + 1024 + 256;
+constexpr int TM_BOX = 128 * TM_BOXK;                    // doubles per A box (16 KB)
+// stage = A lo, A hi (128 rows each) + B lo, B hi (BN rows each), KC = 32
+__host__ __device__ constexpr int tm_stage(int bn) { return 2 * TM_BOX + 2 * bn * TM_BOXK; }
+__host__ __device__ constexpr int tm_smem(int bn, int nst) { return nst * tm_stage(bn) * 8 + 1024 + 256; }
 static_assert(KC == 2 * TM_BOXK, "stage = two boxes per operand");
 
 // 2-D tiled TMA load: box (c0 .. c0+16, c1 .. c1+128) of the tensor described by `tmap`
@@ -445,10 +465,17 @@ struct StageHdr {   // what a filled stage contains
   int valid;        // valid k in this chunk (<= KC)
 };
 
-__global__ void __launch_bounds__(384, 1)
+// BN = 128: 8 consumer warps + producer warpgroup = 384 threads, 3 stages, one CTA per SM.
+// BN = 64 : 4 consumer warps + producer warpgroup = 256 threads, 2 stages, TWO CTAs per SM: while
+//           one CTA runs the (DMMA-idle) scatter epilogue of a tile the other keeps the pipe busy.
+template <int BN, int TM_ST>
+__global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
     k_tile_tma(const TileTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, double* __restrict__ arena,
-               DevMaps mp, const unsigned char* __restrict__ tmaps) {
-  constexpr int BM = 128, BN = 128, WM = 64, WN = 32, FM = WM / 8, FN = WN / 8;
+               DevMaps mp, const unsigned char* __restrict__ tmaps, const unsigned char* __restrict__ tmaps_b) {
+  constexpr int WM = 64, WN = 32, FM = WM / 8, FN = WN / 8;
+  constexpr int NCW = (128 / WM) * (BN / WN);              // consumer warps
+  constexpr int TM_STAGE = tm_stage(BN);
+  constexpr int TM_BBOX = BN * TM_BOXK;
   extern __shared__ __align__(16) double sm_raw[];
   // the swizzle pattern is a function of the shared address: boxes must start 1024-byte aligned
   double* sm = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
@@ -459,7 +486,7 @@ __global__ void __launch_bounds__(384, 1)
   if (tid == 0) {
     for (int s = 0; s < TM_ST; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, 8);
+      mbar_init(empty + s, NCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -467,9 +494,9 @@ __global__ void __launch_bounds__(384, 1)
 
   // 3 warpgroups: two of consumers, one for the producer (only its first warp works).  The
   // register file is re-partitioned between them: 168 regs/thread at launch (384 threads).
-  if (warp >= 8) {
+  if (warp >= NCW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp != 8) return;
+    if (warp != NCW) return;
     // ------------------------------------------------ producer
     int it = 0;  // stages filled so far
     for (;;) {
@@ -487,6 +514,7 @@ __global__ void __launch_bounds__(384, 1)
       }
       const TileTask t = tasks[ti];
       const unsigned char* tm = tmaps + (size_t)t.node * 128;
+      const unsigned char* tmb = tmaps_b + (size_t)t.node * 128;
       const int nch = (t.kk + KC - 1) / KC;
       for (int ch = 0; ch < nch; ++ch, ++it) {
         int s = it % TM_ST;
@@ -498,8 +526,8 @@ __global__ void __launch_bounds__(384, 1)
           int kc = t.k0 + ch * KC;
           tma_load_2d(st, tm, kc, t.i0, full + s);
           tma_load_2d(st + TM_BOX, tm, kc + TM_BOXK, t.i0, full + s);
-          tma_load_2d(st + 2 * TM_BOX, tm, kc, t.j0, full + s);
-          tma_load_2d(st + 3 * TM_BOX, tm, kc + TM_BOXK, t.j0, full + s);
+          tma_load_2d(st + 2 * TM_BOX, tmb, kc, t.j0, full + s);
+          tma_load_2d(st + 2 * TM_BOX + TM_BBOX, tmb, kc + TM_BOXK, t.j0, full + s);
         }
         __syncwarp();
       }
@@ -508,7 +536,10 @@ __global__ void __launch_bounds__(384, 1)
   }
 
   // -------------------------------------------------- consumers
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  if (BN == 128)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  else
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
   const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
   const int rho = lane >> 2, lk = lane & 3;
   // fragment row / column rho of an 8-group is read from shared row sigma(rho) (see header):
@@ -538,12 +569,13 @@ __global__ void __launch_bounds__(384, 1)
       if (h.valid == KC) {
 #pragma unroll
         for (int k4 = 0; k4 < KC; k4 += 4) {
-          const int x = (k4 >> 4) * TM_BOX + (((((k4 & 15) >> 1) | hsel) ^ sig) << 1);
+          const int xs_ = ((((k4 & 15) >> 1) | hsel) ^ sig) << 1;
+          const int x = (k4 >> 4) * TM_BOX + xs_, xb = (k4 >> 4) * TM_BBOX + xs_;
           double af[FM], bf[FN];
 #pragma unroll
           for (int i = 0; i < FM; ++i) af[i] = a[i * 8 * TM_BOXK + x];
 #pragma unroll
-          for (int j = 0; j < FN; ++j) bf[j] = b[j * 8 * TM_BOXK + x];
+          for (int j = 0; j < FN; ++j) bf[j] = b[j * 8 * TM_BOXK + xb];
 #pragma unroll
           for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -552,12 +584,13 @@ __global__ void __launch_bounds__(384, 1)
       } else {
         for (int k4 = 0; k4 < h.valid; k4 += 4) {
           const bool kok = k4 + lk < h.valid;
-          const int x = (k4 >> 4) * TM_BOX + (((((k4 & 15) >> 1) | hsel) ^ sig) << 1);
+          const int xs_ = ((((k4 & 15) >> 1) | hsel) ^ sig) << 1;
+          const int x = (k4 >> 4) * TM_BOX + xs_, xb = (k4 >> 4) * TM_BBOX + xs_;
           double af[FM], bf[FN];
 #pragma unroll
           for (int i = 0; i < FM; ++i) af[i] = kok ? a[i * 8 * TM_BOXK + x] : 0.0;
 #pragma unroll
-          for (int j = 0; j < FN; ++j) bf[j] = kok ? b[j * 8 * TM_BOXK + x] : 0.0;
+          for (int j = 0; j < FN; ++j) bf[j] = kok ? b[j * 8 * TM_BOXK + xb] : 0.0;
 #pragma unroll
           for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -1023,7 +1056,8 @@ void kernels_init() {
   CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
   CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
   CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
-  CK(cudaFuncSetAttribute(k_tile_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_TMA));
+  CK(cudaFuncSetAttribute(k_tile_tma<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(128, 3)));
+  CK(cudaFuncSetAttribute(k_tile_tma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(64, 2)));
   CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_bwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
@@ -1046,11 +1080,17 @@ void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* inf
   if (count > 0) k_panel<true><<<(unsigned)count, PANEL_THREADS, SMEM_PANEL, st>>>(tasks, arena, info, pcount, dbg);
 }
 void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
-                      const void* tmaps, cudaStream_t st) {
+                      const void* tmaps, const void* tmaps_b, int bn, cudaStream_t st) {
   if (count <= 0) return;
-  unsigned grid = (unsigned)std::min<i64>(count, 148);
-  k_tile_tma<<<grid, 384, SMEM_TILE_TMA, st>>>(tasks, (int)count, counter, arena, maps,
-                                               (const unsigned char*)tmaps);
+  if (bn == 128) {
+    unsigned grid = (unsigned)std::min<i64>(count, 148);
+    k_tile_tma<128, 3><<<grid, 384, tm_smem(128, 3), st>>>(tasks, (int)count, counter, arena, maps,
+                                                          (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
+  } else {
+    unsigned grid = (unsigned)std::min<i64>(count, 296);
+    k_tile_tma<64, 2><<<grid, 256, tm_smem(64, 2), st>>>(tasks, (int)count, counter, arena, maps,
+                                                        (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
+  }
 }
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
   if (count <= 0) return;

@@ -119,6 +119,7 @@ struct RefBlock {    // spllt_block, 1-based (src/spllt_data_mod.F90:123-172)
 struct Analysis {
   int n = 0, nb = 0, nemin = 32, ncpu = 1, prune = 1, min_width_blas = 8;
   int rank = 0, world = 1;   // multi-GPU partition (partition_tree)
+  int tile_n = 128;          // N extent of the large tiles: 128 (one CTA/SM) or 64 (two CTAs/SM)
   i64 nnz = 0;               // entries of the user's lower triangle
   Symbolic sym;
   std::vector<int> porder;   // porder[p] = variable at pivot position p (0-based both)
