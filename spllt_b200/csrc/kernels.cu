@@ -722,37 +722,84 @@ constexpr int SPL = SP + 1;
 constexpr int DIAG_THREADS = 512;
 
 // Forward: solve L_cc x = b for one block column (w x w lower triangle, row-major), 64 columns
-// at a time: (a) triangular solve of the 64 x 64 diagonal block -- one warp per right-hand side,
-// each lane owns rows l and l + 32, pivot broadcast by shuffle, reciprocals precomputed so the
-// per-column chain is multiply + shuffle + FMA; (b) the rows of the triangle below it:
-// warp-per-row dot products with coalesced 512-byte row segments, four rows in flight per warp.
+// at a time, left-looking: (a) b_p -= L[p rows, 0..p0) x[0..p0): 16 warps x 4 rows, every
+// row's loads (coalesced 256-byte segments) in flight together, while the 64 x 64 diagonal
+// block is fetched with cp.async; (b) triangular solve of the diagonal block -- one warp per
+// right-hand side, each lane owns rows l and l + 32, pivot broadcast by shuffle, reciprocals
+// precomputed so the per-column chain is multiply + shuffle + FMA.
 template <int RC>
 __global__ void __launch_bounds__(DIAG_THREADS) k_fwd_diag(const SolveBcol* __restrict__ bcs,
                                                            const double* __restrict__ arena, double* __restrict__ xw,
                                                            int nrhs) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const SolveBcol b = bcs[blockIdx.x];
   const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = DIAG_THREADS / 32;
   const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
-  double* xs = sm;                 // [RC][wp]
-  double* Ls = sm + RC * wp;       // [SP][SPL]
+  double* Ls = sm;                 // [SP][SPL]   (first: 8-byte cp.async destinations stay aligned)
+  double* xs = sm + SP * SPL;      // [RC][wp]
   const double* L = arena + b.off + (i64)b.r0 * b.ld + b.r0;
   double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
   for (int idx = tid; idx < w * RC; idx += DIAG_THREADS) {
     int k = idx / RC, q = idx - k * RC;
     xs[q * wp + k] = (q < nr) ? xg[(i64)k * nrhs + q] : 0.0;
   }
+  __syncthreads();
   for (int p0 = 0; p0 < w; p0 += SP) {
     const int pw = min(SP, w - p0);
-    __syncthreads();
-    {
+    {  // diagonal block -> Ls (asynchronous; consumed after the barrier below)
       const int cc = tid & (SP - 1), rr = tid >> 6;
-#pragma unroll 8
-      for (int r = rr; r < pw; r += DIAG_THREADS / SP)
-        Ls[r * SPL + cc] = (cc <= r && cc < pw) ? L[(i64)(p0 + r) * b.ld + p0 + cc] : 0.0;
+      for (int r = rr; r < pw; r += DIAG_THREADS / SP) {
+        bool ok = cc <= r && cc < pw;
+        cp_async8(Ls + r * SPL + cc, ok ? L + (i64)(p0 + r) * b.ld + p0 + cc : L, ok ? 8 : 0);
+      }
+      cp_commit();
     }
+    // (a) left-looking update of the panel's rows
+    for (int rb = warp * 4; rb < pw; rb += 4 * NW) {
+      double acc[4][RC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < RC; ++q) acc[u][q] = 0.0;
+      for (int kb = 0; kb < p0; kb += 256) {
+        double l[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double* lr = L + (i64)(p0 + min(rb + u, pw - 1)) * b.ld;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int k = kb + j * 32 + lane;
+            l[u][j] = (k < p0 && rb + u < pw) ? lr[k] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int k = min(kb + j * 32 + lane, w - 1);
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            double xv = xs[q * wp + k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u][q] += l[u][j] * xv;
+          }
+        }
+      }
+      if (p0 > 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            double v = acc[u][q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+            if (lane == 0 && rb + u < pw && q < nr) xs[q * wp + p0 + rb + u] -= v;
+          }
+      }
+    }
+    cp_wait<0>();
     __syncthreads();
-    for (int q = warp; q < nr; q += DIAG_THREADS / 32) {
+    // (b) triangular solve of the diagonal block
+    for (int q = warp; q < nr; q += NW) {
       const int i0 = lane, i1 = lane + 32;
       double x0 = (i0 < pw) ? xs[q * wp + p0 + i0] : 0.0, x1 = (i1 < pw) ? xs[q * wp + p0 + i1] : 0.0;
       const double d0 = (i0 < pw) ? 1.0 / Ls[i0 * SPL + i0] : 0.0, d1 = (i1 < pw) ? 1.0 / Ls[i1 * SPL + i1] : 0.0;
@@ -760,42 +807,18 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_fwd_diag(const SolveBcol* __re
         double xk = __shfl_sync(FULL, x0 * d0, k);
         if (lane == k) x0 = xk;
         if (i0 > k) x0 -= Ls[i0 * SPL + k] * xk;
-        x1 -= Ls[i1 * SPL + k] * xk;      // rows >= 32 are below every pivot < 32 (zero rows beyond pw)
+        if (i1 < pw) x1 -= Ls[i1 * SPL + k] * xk;
       }
       for (int k = 32; k < pw; ++k) {
         double xk = __shfl_sync(FULL, x1 * d1, k - 32);
         if (lane == k - 32) x1 = xk;
-        if (i1 > k) x1 -= Ls[i1 * SPL + k] * xk;
+        if (i1 > k && i1 < pw) x1 -= Ls[i1 * SPL + k] * xk;
       }
       if (i0 < pw) xs[q * wp + p0 + i0] = x0;
       if (i1 < pw) xs[q * wp + p0 + i1] = x1;
     }
     __syncthreads();
-    const int below = p0 + pw;
-    for (int ib = below + warp; ib < w; ib += 8 * (DIAG_THREADS / 32)) {
-      double l0[8], l1[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int i = ib + u * (DIAG_THREADS / 32);
-        const double* lr = L + (i64)min(i, w - 1) * b.ld + p0;
-        l0[u] = (i < w && lane < pw) ? lr[lane] : 0.0;
-        l1[u] = (i < w && lane + 32 < pw) ? lr[lane + 32] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int i = ib + u * (DIAG_THREADS / 32);
-#pragma unroll
-        for (int q = 0; q < RC; ++q) {
-          double sacc = ((lane < pw) ? l0[u] * xs[q * wp + p0 + lane] : 0.0) +
-                        ((lane + 32 < pw) ? l1[u] * xs[q * wp + p0 + lane + 32] : 0.0);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(FULL, sacc, o);
-          if (lane == 0 && i < w && q < nr) xs[q * wp + i] -= sacc;
-        }
-      }
-    }
   }
-  __syncthreads();
   for (int idx = tid; idx < w * nr; idx += DIAG_THREADS) {
     int k = idx / nr, q = idx - k * nr;
     xg[(i64)k * nrhs + q] = xs[q * wp + k];
@@ -941,21 +964,21 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const SolveUpd* __restrict__ up
   }
 }
 
-// Backward: solve L_cc^T x = b, panels from last to first: (a) x_p -= L[below, p]^T x_below
-// (rows split over the warps, lanes over the panel's columns, cross-warp reduction in shared
-// memory), (b) transposed triangular solve of the diagonal block.
+// Backward: solve L_cc^T x = b, panels from last to first, right-looking: (a) transposed
+// triangular solve of the 64 x 64 diagonal block (fetched with cp.async during the previous
+// panel's update); (b) x[0..p0) -= L[p rows, 0..p0)^T x_p: thread per column, coalesced across
+// threads, 32 row loads in flight per thread.
 template <int RC>
 __global__ void __launch_bounds__(DIAG_THREADS) k_bwd_diag(const SolveBcol* __restrict__ bcs,
                                                            const double* __restrict__ arena, double* __restrict__ xw,
                                                            int nrhs) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const SolveBcol b = bcs[blockIdx.x];
   const int w = b.w, wp = w + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NW = DIAG_THREADS / 32;
   const int rc0 = blockIdx.y * RC, nr = min(RC, nrhs - rc0);
-  double* xs = sm;                    // [RC][wp]
-  double* Ls = sm + RC * wp;          // [SP][SPL]
-  double* red = Ls + SP * SPL;        // [NW][RC][SP]
+  double* Ls = sm;                    // [SP][SPL]
+  double* xs = sm + SP * SPL;         // [RC][wp]
   const double* L = arena + b.off + (i64)b.r0 * b.ld + b.r0;
   double* xg = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
   for (int idx = tid; idx < w * RC; idx += DIAG_THREADS) {
@@ -964,53 +987,18 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_bwd_diag(const SolveBcol* __re
   }
   const int npan = (w + SP - 1) / SP;
   for (int ip = npan - 1; ip >= 0; --ip) {
-    const int p0 = ip * SP, pw = min(SP, w - p0), below = p0 + pw;
-    __syncthreads();
+    const int p0 = ip * SP, pw = min(SP, w - p0);
     {
       const int cc = tid & (SP - 1), rr = tid >> 6;
-#pragma unroll 8
-      for (int r = rr; r < pw; r += DIAG_THREADS / SP)
-        Ls[r * SPL + cc] = (cc <= r && cc < pw) ? L[(i64)(p0 + r) * b.ld + p0 + cc] : 0.0;
-    }
-    // (a) partial column sums over this warp's rows
-    double a0[RC], a1[RC];
-#pragma unroll
-    for (int q = 0; q < RC; ++q) a0[q] = a1[q] = 0.0;
-    for (int ib = below + warp; ib < w; ib += 8 * NW) {
-      double l0[8], l1[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int i = ib + u * NW;
-        const double* lr = L + (i64)min(i, w - 1) * b.ld + p0;
-        l0[u] = (i < w && lane < pw) ? lr[lane] : 0.0;
-        l1[u] = (i < w && lane + 32 < pw) ? lr[lane + 32] : 0.0;
+      for (int r = rr; r < pw; r += DIAG_THREADS / SP) {
+        bool ok = cc <= r && cc < pw;
+        cp_async8(Ls + r * SPL + cc, ok ? L + (i64)(p0 + r) * b.ld + p0 + cc : L, ok ? 8 : 0);
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int i = min(ib + u * NW, w - 1);
-#pragma unroll
-        for (int q = 0; q < RC; ++q) {
-          double xi = xs[q * wp + i];
-          a0[q] += l0[u] * xi;
-          a1[q] += l1[u] * xi;
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < RC; ++q) {
-      red[(warp * RC + q) * SP + lane] = a0[q];
-      red[(warp * RC + q) * SP + lane + 32] = a1[q];
+      cp_commit();
+      cp_wait<0>();
     }
     __syncthreads();
-    for (int idx = tid; idx < RC * SP; idx += DIAG_THREADS) {
-      int q = idx / SP, k = idx - q * SP;
-      double ssum = 0.0;
-#pragma unroll
-      for (int u = 0; u < NW; ++u) ssum += red[(u * RC + q) * SP + k];
-      if (k < pw && q < nr) xs[q * wp + p0 + k] -= ssum;
-    }
-    __syncthreads();
-    // (b) transposed solve: x_k = x_k / L_kk, then x_i -= L[k][i] x_k for i < k
+    // (a) transposed solve: x_k = x_k / L_kk, then x_i -= L[k][i] x_k for i < k
     for (int q = warp; q < nr; q += NW) {
       const int i0 = lane, i1 = lane + 32;
       double x0 = (i0 < pw) ? xs[q * wp + p0 + i0] : 0.0, x1 = (i1 < pw) ? xs[q * wp + p0 + i1] : 0.0;
@@ -1029,8 +1017,33 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_bwd_diag(const SolveBcol* __re
       if (i0 < pw) xs[q * wp + p0 + i0] = x0;
       if (i1 < pw) xs[q * wp + p0 + i1] = x1;
     }
+    __syncthreads();
+    // (b) columns left of the panel
+    for (int k = tid; k < p0; k += DIAG_THREADS) {
+      double acc[RC];
+#pragma unroll
+      for (int q = 0; q < RC; ++q) acc[q] = 0.0;
+      const double* lc = L + (i64)p0 * b.ld + k;
+      for (int r0 = 0; r0 < pw; r0 += 16) {
+        double l[16];
+        // unconditional (clamped) loads so that all 16 are issued back to back
+#pragma unroll
+        for (int r = 0; r < 16; ++r) l[r] = lc[(i64)min(r0 + r, pw - 1) * b.ld];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            double xv = (r0 + r < pw) ? xs[q * wp + p0 + r0 + r] : 0.0;
+            acc[q] += l[r] * xv;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RC; ++q)
+        if (q < nr) xs[q * wp + k] -= acc[q];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int idx = tid; idx < w * nr; idx += DIAG_THREADS) {
     int k = idx / nr, q = idx - k * nr;
     xg[(i64)k * nrhs + q] = xs[q * wp + k];
@@ -1110,7 +1123,7 @@ void launch_permute_out(double* x, int ldx, const int* porder, const double* xw,
 }
 
 static inline int solve_smem(int maxw, int rc, bool tri) {
-  return (rc * (maxw + 1) + (tri ? SP * SPL + (DIAG_THREADS / 32) * rc * SP : 0)) * 8;
+  return (rc * (maxw + 1) + (tri ? SP * SPL : 0)) * 8;
 }
 static int g_maxw = 1024;
 void set_solve_maxw(int w) { g_maxw = w; }
