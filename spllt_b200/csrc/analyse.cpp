@@ -414,18 +414,24 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
 
   // ---- level sets, one pass per phase (phase 0: nodes owned by this rank, phase 1: shared top)
   std::vector<TileTask> ts, tl;
-  std::vector<Region> regions;
+  std::vector<Region> regions, regions_bg;
   int cur_phase = 0;
   auto add_tiles = [&](Analysis&, std::vector<TileTask>&, std::vector<TileTask>&, const HNode& nd, int jbeg, int jend,
                        int ibeg_min, int iend, int k0, int kk, int src, int) {
     if (jend <= jbeg || iend <= jbeg) return;
     regions.push_back({&nd, jbeg, jend, ibeg_min, iend, k0, kk, src});
   };
-  auto flush_tiles = [&](int depth, int tag) {
+  // Deferring the non-urgent inter-node updates to a low-priority stream is implemented and
+  // parity-tested but did not pay off on B200 (FP64 tile CTAs are register-file bound, so the
+  // panel kernels cannot share an SM with two of them): opt-in.
+  const bool defer = getenv("SPLLT_B200_DEFER") != nullptr;
+  auto flush_tiles = [&](int depth, int tag, int stream = 0, int deadline = 0) {
+    std::vector<Region>& regions_ = stream ? regions_bg : regions;
     // Tile size per launch: 128 x 128 tiles only pay off when the launch fills the machine;
     // a launch with less than a wave of them is latency bound and runs faster on 64 x 64
     // tiles spread over more SMs.  Tasks are sorted by decreasing work so the tail of every
     // launch consists of small tiles.
+    auto& regions = regions_;
     i64 nlarge = 0;
     std::vector<char> big(regions.size(), 0);
     for (size_t i = 0; i < regions.size(); ++i) {
@@ -443,12 +449,12 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     std::stable_sort(ts.begin(), ts.end(), [&](const TileTask& a, const TileTask& b) { return work(a) > work(b); });
     std::stable_sort(tl.begin(), tl.end(), [&](const TileTask& a, const TileTask& b) { return work(a) > work(b); });
     if (!ts.empty()) {
-      A.launches.push_back({L_TILE_S, depth, (i64)A.tile_tasks.size(), (i64)ts.size(), cur_phase, tag});
+      A.launches.push_back({L_TILE_S, depth, (i64)A.tile_tasks.size(), (i64)ts.size(), cur_phase, tag, stream, deadline});
       A.tile_tasks.insert(A.tile_tasks.end(), ts.begin(), ts.end());
       ts.clear();
     }
     if (!tl.empty()) {
-      A.launches.push_back({L_TILE_L, depth, (i64)A.tile_tasks.size(), (i64)tl.size(), cur_phase, tag});
+      A.launches.push_back({L_TILE_L, depth, (i64)A.tile_tasks.size(), (i64)tl.size(), cur_phase, tag, stream, deadline});
       A.tile_tasks.insert(A.tile_tasks.end(), tl.begin(), tl.end());
       tl.clear();
     }
@@ -482,6 +488,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
       if (par >= 0 && mine(par)) t0[par] = std::max(t0[par], tend);
     }
     std::vector<std::vector<Step>> at(nslots);
+    int bg_deadline = 1 << 30;
     for (int s = 0; s < nn; ++s) {
       if (!mine(s)) continue;
       int t = t0[s];
@@ -524,13 +531,39 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         } else {
           // a3: the finished block column updates the node's later block columns (K = w)
           if (st.c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
-          // a4: the finished node updates its ancestors (K = n)
-          if (st.c + 1 == nd.nc && nd.m > nd.n)
-            add_tiles(A, ts, tl, nd, nd.n, nd.m, 0, nd.m, 0, nd.n, st.node, tile_l_min);
+          // a4: the finished node updates its ancestors (K = n).  Only the columns that belong
+          // to an ancestor whose first panel runs in the very next slot are on the critical path;
+          // the rest is deferred to the background stream with the slot of the first ancestor
+          // that needs it as its deadline.
+          if (st.c + 1 == nd.nc && nd.m > nd.n) {
+            const int* idx = A.index.data() + nd.idx_off;
+            int r = nd.n, split = nd.n, dl = 1 << 30;
+            bool first = true;
+            while (r < nd.m) {
+              int a = A.col2node[idx[r]];
+              int r1 = r;
+              while (r1 < nd.m && idx[r1] <= A.nodes[a].en) ++r1;
+              int need = mine(a) ? t0[a] : (1 << 30);   // other phase: after the exchange step
+              if (first && need <= d + 1) split = r1;   // urgent: the parent starts in the next slot
+              else dl = std::min(dl, need);
+              first = false;
+              r = r1;
+            }
+            if (!defer) split = nd.m;
+            if (split > nd.n) add_tiles(A, ts, tl, nd, nd.n, split, 0, nd.m, 0, nd.n, st.node, tile_l_min);
+            if (split < nd.m) {
+              regions_bg.push_back({&nd, split, nd.m, 0, nd.m, 0, nd.n, st.node});
+              bg_deadline = std::min(bg_deadline, dl);
+            }
+          }
         }
       }
-      A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0});
+      A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0, 0, 0});
       flush_tiles(d, 4);
+      if (!regions_bg.empty()) {
+        flush_tiles(d, 5, 1, bg_deadline);
+        bg_deadline = 1 << 30;
+      }
     }
   }
 }

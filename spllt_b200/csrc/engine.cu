@@ -60,6 +60,9 @@ void Engine::upload_tables() {
   if (!stream) stream = own;
   if (!side) {
     CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&bg, cudaStreamNonBlocking, lo));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
@@ -144,13 +147,15 @@ void Engine::ensure_solve_buffers(int nrhs) {
   xw_nrhs = nrhs;
 }
 
-void Engine::launch_one(const Launch& L, cudaStream_t st) {
+void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
   DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
   switch (L.kind) {
     case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, d_counters + A->launches.size(), st); break;
     case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
     case L_TILE_L:
-      if (use_tma)   // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
+      if (use_tma && background && A->tile_n == 64)
+        launch_tiles_tma_bg(d_tile + L.begin, L.count, arena, mp, d_tmaps, d_tmaps_b, st);
+      else if (use_tma)   // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
         launch_tiles_tma(d_tile + L.begin, L.count, d_counters + (&L - A->launches.data()), arena, mp, d_tmaps,
                          d_tmaps_b, A->tile_n, st);
       else
@@ -172,26 +177,71 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     if (S.world > 1 && S.rank != 0 && S.arena > S.top_begin)
       CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
   }
-  // The small-tile and large-tile launches of one slot write disjoint destinations (or use
-  // atomics): fork them onto two streams so the latency-bound small launch overlaps the
-  // throughput-bound one.  (Works inside stream capture: the side stream joins the graph.)
+  // Streams (all of it is captured into one CUDA graph):
+  //   st   : panel launch of every slot + the updates on the critical path;
+  //   side : the small-tile launch of a slot, forked so that it overlaps the large-tile one
+  //          (disjoint destinations or atomics);
+  //   bg   : low priority; deferred inter-node updates (Launch::stream == 1).  A background
+  //          launch starts after the panel of its slot and is joined right before the panel
+  //          of its deadline slot.
   const bool fork = overlap_tiles && side != nullptr;
+  struct Pending {
+    int deadline;
+    cudaEvent_t ev;
+  };
+  std::vector<Pending> pending;
+  size_t ev_used = 0;
+  auto next_event = [&]() {
+    if (ev_used == ev_pool.size()) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev_pool.push_back(e);
+    }
+    return ev_pool[ev_used++];
+  };
+  auto join_bg = [&](int slot) {   // wait for every background launch whose deadline is <= slot
+    int last = -1;
+    for (size_t k = 0; k < pending.size(); ++k)
+      if (pending[k].deadline <= slot) last = (int)k;
+    if (last < 0) return;
+    CK(cudaStreamWaitEvent(st, pending[last].ev, 0));   // bg is in-order: covers the earlier ones
+    pending.erase(pending.begin(), pending.begin() + last + 1);
+  };
+  cudaEvent_t ev_panel = nullptr;
   for (size_t i = 0; i < S.launches.size(); ++i) {
     const Launch& L = S.launches[i];
     if (phase >= 0 && L.phase != phase) continue;
+    if (L.stream == 1 && fork) {
+      CK(cudaStreamWaitEvent(bg, ev_panel, 0));
+      launch_one(L, bg, true);
+      cudaEvent_t e = next_event();
+      CK(cudaEventRecord(e, bg));
+      pending.push_back({L.deadline, e});
+      continue;
+    }
+    if (L.kind == L_PANEL) {
+      join_bg(L.depth);
+      launch_one(L, st, false);
+      if (fork) {
+        ev_panel = next_event();
+        CK(cudaEventRecord(ev_panel, st));
+      }
+      continue;
+    }
     if (fork && L.kind == L_TILE_S && i + 1 < S.launches.size() && S.launches[i + 1].kind == L_TILE_L &&
-        S.launches[i + 1].depth == L.depth && S.launches[i + 1].phase == L.phase) {
+        S.launches[i + 1].depth == L.depth && S.launches[i + 1].phase == L.phase && S.launches[i + 1].stream == 0) {
       CK(cudaEventRecord(ev_fork, st));
       CK(cudaStreamWaitEvent(side, ev_fork, 0));
-      launch_one(L, side);
-      launch_one(S.launches[i + 1], st);
+      launch_one(L, side, false);
+      launch_one(S.launches[i + 1], st, false);
       CK(cudaEventRecord(ev_join, side));
       CK(cudaStreamWaitEvent(st, ev_join, 0));
       ++i;
       continue;
     }
-    launch_one(L, st);
+    launch_one(L, st, false);
   }
+  join_bg(1 << 30);
 }
 
 void Engine::factor(const double* dval) {
@@ -246,7 +296,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
       CK(cudaMalloc(&dbg, dbg_count * 8 * sizeof(long long)));
       launch_panel_dbg(d_panel + L.begin, L.count, arena, d_info, d_counters + S.launches.size(), dbg, st);
     } else {
-      launch_one(L, st);
+      launch_one(L, st, false);
     }
     CK(cudaEventRecord(ev[i + 2], st));
   }
@@ -467,6 +517,10 @@ void Engine::release() {
   own = nullptr;
   if (side) {
     cudaStreamDestroy(side);
+    cudaStreamDestroy(bg);
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    ev_pool.clear();
+    bg = nullptr;
     cudaEventDestroy(ev_fork);
     cudaEventDestroy(ev_join);
     side = nullptr;

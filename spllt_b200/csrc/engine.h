@@ -30,6 +30,8 @@ struct Engine {
   cudaStream_t stream = nullptr, own = nullptr;
   bool own_stream = false;
   cudaStream_t side = nullptr;  // second stream: small-tile launches overlap the large-tile launch of their slot
+  cudaStream_t bg = nullptr;    // low-priority stream: deferred inter-node updates
+  std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_tiles = true;
   int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
@@ -72,7 +74,7 @@ struct Engine {
   void factor(const double* dval);
   void factor_host(const double* val);
   void profile_factor(const double* dval, double* ms5, const char* csv);
-  void launch_one(const Launch& L, cudaStream_t st);
+  void launch_one(const Launch& L, cudaStream_t st, bool background);
   void enqueue_solve(int nrhs, int job, cudaStream_t st);
   void solve(double* dx, int ldx, int nrhs, int job);
   void profile_solve(double* dx, int ldx, int nrhs, double* ms4, const char* csv);

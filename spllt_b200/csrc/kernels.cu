@@ -104,7 +104,7 @@ constexpr int PLD = IB + 1;   // X rows: conflict-free when thread r reads X[r][
 constexpr int LTD = IB + 2;   // Lt rows: even, so (c*LTD + j) is 16-byte aligned for even j
 constexpr int PB = 16;        // register block
 constexpr int PANEL_THREADS = 128 + TRSM_ROWS;
-constexpr int SMEM_PANEL = (IB * LTD + IB * PLD + TRSM_ROWS * PLD + 2 * IB + IB + 8) * 8;
+constexpr int SMEM_PANEL = (IB * LTD + TRSM_ROWS * PLD + 2 * IB + IB + 8) * 8;
 
 template <bool DBG>
 __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
@@ -112,8 +112,9 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
                                                           long long* __restrict__ dbg) {
   extern __shared__ __align__(16) double sm[];
   double* Lt = sm;                        // [IB][LTD]   Lt[c][r] = L[r][c]
-  double* S = Lt + IB * LTD;              // [IB][PLD]   staged diagonal block
-  double* X = S + IB * PLD;               // [TRSM_ROWS][PLD]
+  // the un-factorized block is staged in the same buffer, in the same (transposed) layout:
+  // column k is consumed into registers before step k overwrites it with L's column k
+  double* X = Lt + IB * LTD;              // [TRSM_ROWS][PLD]
   double* col = X + TRSM_ROWS * PLD;      // [2][IB]
   double* dinv = col + 2 * IB;            // [IB]
   unsigned long long* blk_done = reinterpret_cast<unsigned long long*>(dinv + IB);  // [4]
@@ -126,11 +127,13 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
     for (int i = 0; i < IB / PB; ++i) mbar_init(blk_done + i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {  // diagonal block: lane -> column, no integer division, loads batched
+  {  // diagonal block: lane -> column, PANEL_THREADS / 64 rows per pass, no integer division,
+     // column test hoisted so that the loads of the unrolled passes are issued together
+    static_assert(PANEL_THREADS % IB == 0 && TRSM_ROWS % IB == 0, "copy loops use groups of 64 threads");
     const int cc = tid & (IB - 1), r2 = tid >> 6;
     if (cc < pw) {
 #pragma unroll 8
-      for (int r = r2; r < pw; r += 4) S[r * PLD + cc] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
+      for (int r = r2; r < pw; r += PANEL_THREADS / IB) Lt[cc * LTD + r] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
     }
   }
   __syncthreads();
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
       const int cbase = c0 + h * 8;
       double a[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = (r < pw && cbase + j < pw && cbase + j <= r) ? S[r * PLD + cbase + j] : 0.0;
+      for (int j = 0; j < 8; ++j) a[j] = (r < pw && cbase + j < pw && cbase + j <= r) ? Lt[(cbase + j) * LTD + r] : 0.0;
       if (r >= c0 && r < pw) {
 #pragma unroll 4
         for (int c = 0; c < c0; ++c) {
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
     const int cc = row & (IB - 1), r2 = row >> 6;
     if (cc < pw) {
 #pragma unroll 8
-      for (int r = r2; r < t.nrows; r += 2) X[r * PLD + cc] = gr[(i64)r * t.ld + cc];
+      for (int r = r2; r < t.nrows; r += TRSM_ROWS / IB) X[r * PLD + cc] = gr[(i64)r * t.ld + cc];
     }
   }
   asm volatile("bar.sync 2, %0;" ::"n"(TRSM_ROWS) : "memory");
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
     const int cc = row & (IB - 1), r2 = row >> 6;
     if (cc < pw) {
 #pragma unroll 8
-      for (int r = r2; r < t.nrows; r += 2) gr[(i64)r * t.ld + cc] = X[r * PLD + cc];
+      for (int r = r2; r < t.nrows; r += TRSM_ROWS / IB) gr[(i64)r * t.ld + cc] = X[r * PLD + cc];
     }
   }
   if (DBG && row == 0) dbg[blockIdx.x * 8 + 4] = clock64();
@@ -447,6 +450,7 @@ constexpr int TM_BOX = 128 * TM_BOXK;                    // doubles per A box (1
 // stage = A lo, A hi (128 rows each) + B lo, B hi (BN rows each), KC = 32
 __host__ __device__ constexpr int tm_stage(int bn) { return 2 * TM_BOX + 2 * bn * TM_BOXK; }
 __host__ __device__ constexpr int tm_smem(int bn, int nst) { return nst * tm_stage(bn) * 8 + 1024 + 256; }
+constexpr int SMEM_TILE_BG = 116 * 1024;   // > 227 KB / 2: one background CTA per SM
 static_assert(KC == 2 * TM_BOXK, "stage = two boxes per operand");
 
 // 2-D tiled TMA load: box (c0 .. c0+16, c1 .. c1+128) of the tensor described by `tmap`
@@ -499,10 +503,16 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
     if (warp != NCW) return;
     // ------------------------------------------------ producer
     int it = 0;  // stages filled so far
+    bool first_tile = true;
     for (;;) {
       int ti = 0;
-      if (lane == 0) ti = atomicAdd(counter, 1);
-      ti = __shfl_sync(FULL, ti, 0);
+      if (counter) {
+        if (lane == 0) ti = atomicAdd(counter, 1);
+        ti = __shfl_sync(FULL, ti, 0);
+      } else {   // non-persistent mode (background launches): one tile per CTA
+        ti = first_tile ? (int)blockIdx.x : ntasks;
+        first_tile = false;
+      }
       if (ti >= ntasks) {
         int s = it % TM_ST;
         if (it >= TM_ST) mbar_wait(empty + s, ((it / TM_ST) - 1) & 1);
@@ -1070,7 +1080,7 @@ void kernels_init() {
   CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
   CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
   CK(cudaFuncSetAttribute(k_tile_tma<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(128, 3)));
-  CK(cudaFuncSetAttribute(k_tile_tma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(64, 2)));
+  CK(cudaFuncSetAttribute(k_tile_tma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_BG));
   CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_bwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
@@ -1104,6 +1114,16 @@ void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* ar
     k_tile_tma<64, 2><<<grid, 256, tm_smem(64, 2), st>>>(tasks, (int)count, counter, arena, maps,
                                                         (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
   }
+}
+// Background variant (deferred inter-node updates on the low-priority stream): one tile per
+// CTA (two CTAs per SM), so that SM slots are handed back every few tens of microseconds and
+// the higher-priority panel / small-tile kernels of the main stream (<= 97 KB of shared memory
+// each, i.e. one freed slot) get them first.
+void launch_tiles_tma_bg(const TileTask* tasks, i64 count, double* arena, DevMaps maps, const void* tmaps,
+                         const void* tmaps_b, cudaStream_t st) {
+  if (count <= 0) return;
+  k_tile_tma<64, 2><<<(unsigned)count, 256, tm_smem(64, 2), st>>>(tasks, (int)count, nullptr, arena, maps,
+                                                               (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
 }
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
   if (count <= 0) return;

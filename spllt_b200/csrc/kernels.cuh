@@ -21,6 +21,8 @@ void launch_panel(const PanelTask* tasks, i64 count, double* arena, int* info, i
 void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* info, int* pcount, long long* dbg,
                       cudaStream_t st);
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st);
+void launch_tiles_tma_bg(const TileTask* tasks, i64 count, double* arena, DevMaps maps, const void* tmaps,
+                         const void* tmaps_b, cudaStream_t st);
 // persistent warp-specialised TMA variant of the 128 x 128 tiles; *counter must be 0 at launch
 // bn = 128: 128 x 128 tiles, one CTA per SM; bn = 64: 128 x 64 tiles, two CTAs per SM.
 // tmaps / tmaps_b: per-node tensor maps with 128-row / bn-row boxes.

@@ -26,7 +26,7 @@ typedef int64_t i64;
 
 constexpr int IB = 64;      // inner panel width of the block-column factorization
 constexpr int LDPAD = 4;    // node leading dimension is a multiple of 4 doubles (32 B)
-constexpr int TRSM_ROWS = 128;  // rows per CTA of the panel solve
+constexpr int TRSM_ROWS = 128;  // rows per CTA of the panel solve (multiple of 32)
 constexpr int SOLVE_ROWS = 64;  // rows per CTA of the solve update kernels
 
 // ------------------------------------------------------------------ host symbolic tables
@@ -87,7 +87,9 @@ struct Launch {
   i64 begin;         // first task in the list of this kind
   i64 count;         // tasks (= CTAs)
   int phase;         // multi-GPU: 0 = subtrees owned by this rank, 1 = shared top of the tree
-  int tag;           // diagnostics: 0 panel, 1 inner update (K = IB), 2 outer intra-node, 3 inter-node
+  int tag;           // diagnostics: 0 panel, 4 updates on the critical path, 5 deferred inter-node updates
+  int stream;        // 0 = main; 1 = background stream (deferred inter-node updates)
+  int deadline;      // background launches: the slot whose panel launch must wait for them
 };
 
 // ------------------------------------------------------------------ solve work lists
