@@ -299,9 +299,14 @@ def main():
         tile_ms = prof["tile_s"] + prof["tile_l"]
         n_tile_launch = int(bd[2] + bd[3])
         achieved = tile_flops / tile_ms / 1e9 if tile_ms > 0 else 0.0  # TFLOP/s
-        roofline = {"bound": "tensor", "kernel": "k_tile<128,128,64,32> + k_tile<64,64,32,32> (DMMA.8x8x4)",
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+            traffic = json.load(open(tpath))
+        roofline = {"bound": "tensor", "kernel": "k_tile_tma<64,2> (persistent TMA + DMMA.8x8x4, 128x64 tiles) + "
+                                                 "k_tile<64,64,32,32,2> (small launches)",
                     "achieved": achieved, "peak": peaks["dmma"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["dmma"] if peaks["dmma"] else None, "traffic": None,
+                    "frac": achieved / peaks["dmma"] if peaks["dmma"] else None, "traffic": traffic,
                     "peak_source": "own register-resident mma.sync.m8n8k4.f64 probe on 148 SMs, measured in this "
                                    "run (MEASURED_PEAKS.json has no FP64 figure); DFMA probe = %.1f TFLOP/s" % peaks["dfma"],
                     "flops_per_launch": tile_flops / max(n_tile_launch, 1), "launches": n_tile_launch,
