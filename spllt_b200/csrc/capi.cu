@@ -537,6 +537,7 @@ void spllt_b200_partition(void* akeep, void* fkeep, int rank, int world) {
   e->release();   // work lists change: upload again on next use
   partition_tree(*A, rank, world);
   build_factor_schedule(*A, env_int("SPLLT_B200_TILE_L_MIN", 128));
+  build_solve_schedule(*A);
 }
 int spllt_b200_node_owner(void* akeep, int node) { return AA(akeep)->nodes[node - 1].owner; }
 // host-only variant of spllt_b200_partition (no device state touched): for CPU tests of the mapping
@@ -544,6 +545,7 @@ void spllt_b200_partition_host(void* akeep, int rank, int world) {
   Analysis* A = AA(akeep);
   partition_tree(*A, rank, world);
   build_factor_schedule(*A, env_int("SPLLT_B200_TILE_L_MIN", 128));
+  build_solve_schedule(*A);
 }
 // out[node] = number of inner panels this rank's schedule holds for that node
 void spllt_b200_panel_coverage(void* akeep, long long* out) {

@@ -108,7 +108,8 @@ class DistSpLLT:
         tot = float(per.sum())
         top = float(per[own < 0].sum())
         mine = float(per[own == self.rank].sum())
-        return ("subtree->GPU proportional mapping (%d pruned subtrees), sum all-reduce of the %.2f GB upper-tree "
-                "slice, upper tree (%.0f%% of flops) replicated; rank 0 subtree share %.1f%%"
-                % (int((s.small() == 1).sum()), (self.top_range[1] - self.top_range[0]) * 8 / 1e9,
-                   100 * top / tot, 100 * mine / tot))
+        nsub = int(np.sum((own >= 0) & ((par >= s.nnodes) | (own[np.minimum(par, s.nnodes - 1)] < 0))))
+        return ("subtree->GPU proportional mapping (%d subtrees), sum all-reduce of the %.2f GB upper-tree "
+                "slice, upper tree (%.0f%% of flops) replicated; rank %d subtree share %.1f%%"
+                % (nsub, (self.top_range[1] - self.top_range[0]) * 8 / 1e9, 100 * top / tot, self.rank,
+                   100 * mine / tot))

@@ -60,12 +60,24 @@ def main():
     dist.all_gather(gathered, t)
     for g in gathered:
         assert torch.equal(g.cpu(), torch.from_numpy(own)), "ranks disagree on the subtree mapping"
-    assert np.all((own == -1) == (small == 0)), "upper tree must be shared, subtrees owned"
-    assert np.all((own >= 0) <= (own < world))
-    roots = np.nonzero(small == 1)[0]
-    for r in roots:   # whole subtree has the owner of its root
-        lo = int(s.nodes()[r, 4]) - 1
-        assert np.all(own[lo:r + 1] == own[r])
+    assert np.all(own < world) and np.all(own >= -1)
+    par = s.nodes()[:, 2].astype(np.int64) - 1
+    roots = []
+    for k in range(nn):
+        if own[k] >= 0:
+            # an owned node is either a subtree root (parent shared / none) or has its parent's owner
+            if par[k] >= nn or own[par[k]] < 0:
+                roots.append(k)
+                lo = int(s.nodes()[k, 4]) - 1
+                assert np.all(own[lo:k + 1] == own[k]), "a subtree must have one owner"
+            else:
+                assert own[par[k]] == own[k]
+        else:
+            assert par[k] >= nn or own[par[k]] < 0, "the shared part must be the top of the tree"
+    assert len(set(own[roots])) == min(world, len(roots)) or len(roots) >= world
+    w = s.weight()
+    loads = np.array([sum(int(w[k]) for k in roots if own[k] == r) for r in range(world)], dtype=np.float64)
+    assert loads.max() <= 1.25 * max(loads.mean(), 1.0) or len(roots) <= world
     # ---- work lists: this rank's panels cover exactly its nodes + the shared ones
     cnt = np.zeros(nn, dtype=np.int64)
     s.L.spllt_b200_panel_coverage(s.akeep, cnt.ctypes.data_as(C.POINTER(C.c_longlong)))
@@ -78,7 +90,7 @@ def main():
     if cpu:
         dist.barrier()
         if rank == 0:
-            print("dist_check cpu ok: world %d, %d nodes, %d subtrees" % (world, nn, len(roots)))
+            print("dist_check cpu ok: world %d, %d nodes, %d subtrees, shared flops %.0f%%" % (world, nn, len(roots), 100.0 * (1.0 - loads.sum() / float(w[-1]))))
         dist.destroy_process_group()
         return
 
