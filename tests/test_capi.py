@@ -81,3 +81,16 @@ def test_user_and_natural_ordering():
     s2 = sp.SpLLT(nb=8)
     s2.analyse(n, ptr, row, ordering=sp.ORDER_USER, order=perm)
     assert sorted(s2.order[:n]) == list(range(1, n + 1))
+
+
+def test_matrix_market_reader(tmp_path):
+    """COO -> lower CSC conversion of the driver (role of src/spllt_mod.F90:426-620)."""
+    import scipy.io
+    import scipy.sparse as sps
+    from spllt_b200.driver import read_matrix_market
+    n, ptr, row, val = M.poisson2d(5)
+    a = M.to_dense(n, ptr, row, val)
+    p = tmp_path / "a.mtx"
+    scipy.io.mmwrite(str(p), sps.coo_matrix(a), symmetry="symmetric")
+    n2, ptr2, row2, val2 = read_matrix_market(str(p))
+    assert n2 == n and np.array_equal(ptr2, ptr) and np.array_equal(row2, row) and np.allclose(val2, val)

@@ -258,3 +258,37 @@ def test_full_size_properties_p3d64():
     c = np.asfortranarray(b[:, 0] + 2.0 * b[:, 1])
     s.solve(c, 0)
     assert np.max(np.abs(c - (x[:, 0] + 2.0 * x[:, 1]))) <= 1e-10 * np.abs(c).max()
+
+
+def test_cli_driver(capsys):
+    """drivers/spllt_test.F90 role: flags, timing lines and the backward-error report."""
+    from spllt_b200 import driver
+    rc = driver.main(["--mat", "poisson3d:12", "--nb", "32", "--nrhs", "3", "--ncpu", "2"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "Factor took" in out and "ok for 3/3" in out
+
+
+@pytest.mark.parametrize("nrhs", [2, 7, 8, 9, 33, 64])
+def test_nrhs_sweep(nrhs):
+    """scripts/stress_test.sh sweeps nrhs in {1..10, 16, 32, 64, 128}."""
+    s, o, mat = both(MEDIUM[1])
+    n, ptr, row, val = mat
+    xs, b = rhs_for(mat, nrhs, seed=7)
+    s.prepare_solve(nrhs)
+    x = b.copy(order="F")
+    assert s.solve(x, 0) == 0
+    ok, err = chkerr(n, ptr, row, val, x, b)
+    assert ok == nrhs and err.max() <= BWD_TOL
+
+
+def test_elasticity_config_small():
+    """BASELINE config 4 (27-point, 3 dof) at a size the oracle handles: large fronts relative to n."""
+    case = ("el3d-14-nb256", lambda: M.elasticity3d(14), 256, 4, 1)
+    s, o, mat = both(case)
+    assert_factor_close(s.factor_entries(), o.factor_entries(), lower_mask(s))
+    n, ptr, row, val = mat
+    xs, b = rhs_for(mat, 2)
+    x = b.copy(order="F")
+    s.prepare_solve(2)
+    s.solve(x, 0)
+    assert chkerr(n, ptr, row, val, x, b)[0] == 2
