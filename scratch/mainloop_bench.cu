@@ -1,0 +1,91 @@
+// DMMA mainloop microbenchmark: 128x64 tile per CTA (4 consumer warps, warp tile 64x32), data
+// resident in shared memory (swizzled layout as in k_tile_tma), repeated `iters` stages.
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+constexpr int TM_BOXK = 16, TM_BOX = 128 * 16, KC = 32;
+template <int VAR>
+__global__ void __launch_bounds__(128, 2) k(double* out, int iters) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int FM = 8, FN = 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 2 * TM_BOX + 2 * 64 * 16; i += 128) sm[i] = 1.0 + (i % 7) * 1e-3;
+  __syncthreads();
+  const int wm0 = (warp / 2) * 64, wn0 = (warp % 2) * 32;
+  const int rho = lane >> 2, lk = lane & 3;
+  const int sig = ((rho & 3) << 1) | (rho >> 2);
+  double acc[FM][FN][2];
+  for (int i = 0; i < FM; ++i) for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0;
+  const double* a = sm + (wm0 + sig) * TM_BOXK + (lk & 1);
+  const double* b = sm + 2 * TM_BOX + (wn0 + sig) * TM_BOXK + (lk & 1);
+  const int hsel = lk >> 1;
+  for (int it = 0; it < iters; ++it) {
+    if (VAR == 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < KC; k4 += 4) {
+        const int xs_ = ((((k4 & 15) >> 1) | hsel) ^ sig) << 1;
+        const int x = (k4 >> 4) * TM_BOX + xs_, xb = (k4 >> 4) * (64 * 16) + xs_;
+        double af[FM], bf[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) af[i] = a[i * 8 * TM_BOXK + x];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) bf[j] = b[j * 8 * TM_BOXK + xb];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    } else if (VAR == 1) {
+      // paired-k: one 16-byte load feeds two DMMAs (k = 2*lk and 2*lk+1 of an 8-wide k group)
+      const double* a2 = sm + (wm0 + sig) * TM_BOXK;
+      const double* b2 = sm + 2 * TM_BOX + (wn0 + sig) * TM_BOXK;
+#pragma unroll
+      for (int k8 = 0; k8 < KC; k8 += 8) {
+        const int chunk = (((k8 & 15) >> 1) + lk) ^ sig;     // 16-byte chunk index inside the 128-byte row
+        const int x = (k8 >> 4) * TM_BOX + chunk * 2, xb = (k8 >> 4) * (64 * 16) + chunk * 2;
+        double2 af[FM], bf[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) af[i] = *reinterpret_cast<const double2*>(a2 + i * 8 * TM_BOXK + x);
+#pragma unroll
+        for (int j = 0; j < FN; ++j) bf[j] = *reinterpret_cast<const double2*>(b2 + j * 8 * TM_BOXK + xb);
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) { dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x); dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y); }
+      }
+    } else {
+      // no shared loads at all: pure DMMA with the same accumulator footprint
+      double af = 1.0 + lane * 1e-9, bf = 1.0;
+#pragma unroll
+      for (int k4 = 0; k4 < KC; k4 += 4)
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf);
+    }
+  }
+  double s = 0;
+  for (int i = 0; i < FM; ++i) for (int j = 0; j < FN; ++j) s += acc[i][j][0] + acc[i][j][1];
+  if (s == 123.456) out[0] = s;
+}
+int main() {
+  double* o; cudaMalloc(&o, 64);
+  const int smem = (2 * TM_BOX + 2 * 64 * 16) * 8;
+  cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 4000;
+  for (int var = 0; var < 3; ++var) for (int grid : {148, 296}) {
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaEventRecord(e0);
+      if (var == 0) k<0><<<grid, 128, smem>>>(o, iters); else if (var == 1) k<1><<<grid, 128, smem>>>(o, iters); else k<2><<<grid, 128, smem>>>(o, iters);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+    }
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double fl = (double)grid * 128.0 * 64.0 * KC * 2.0 * iters;
+    printf("var %d grid %d: %.2f TFLOP/s (%s)\n", var, grid, fl / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
+  }
+}

@@ -326,6 +326,7 @@ void ref_blocks(const Analysis& A, std::vector<RefBlock>& out) {
 struct Region {       // lower part of columns [jbeg, jend) x rows [max(j, ibeg_min), iend) of one source node
   const HNode* nd;
   int jbeg, jend, ibeg_min, iend, k0, kk, src;
+  int excl = 0;       // 1: the launch holds this source node only -> scatter without atomics
 };
 
 static i64 count_tiles(const Region& r, int T, int TN) {
@@ -356,7 +357,7 @@ static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r,
       t.src = r.src;
       t.qoff = nd.row_base - nd.n;
       t.node = (int)(&nd - A.nodes.data());
-      t.pad = 0;
+      t.pad = r.excl;
       dst.push_back(t);
       A.tile_flops += 2.0 * T * TN * r.kk;
     }
@@ -489,6 +490,12 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     }
     std::vector<std::vector<Step>> at(nslots);
     int bg_deadline = 1 << 30;
+    std::vector<Region> excl_regions;
+    // Exclusive (atomic-free) launches: implemented and parity-tested, but measured SLOWER than
+    // RED.ADD.F64 (the read-modify-write needs two dependent global round trips per row block,
+    // the RED is fire-and-forget): 64^3 tile time 16.3 -> 24.8 ms.  Opt-in only.
+    const bool excl_ok = (A.nb % 2 == 0) && !getenv("SPLLT_B200_NO_TMA") && getenv("SPLLT_B200_EXCL") && !defer;
+    const i64 excl_min = getenv("SPLLT_B200_EXCL_MIN") ? atoll(getenv("SPLLT_B200_EXCL_MIN")) : 148;
     for (int s = 0; s < nn; ++s) {
       if (!mine(s)) continue;
       int t = t0[s];
@@ -550,7 +557,12 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
               r = r1;
             }
             if (!defer) split = nd.m;
-            if (split > nd.n) add_tiles(A, ts, tl, nd, nd.n, split, 0, nd.m, 0, nd.n, st.node, tile_l_min);
+            // A node whose inter-node update fills the machine on its own gets its own launch:
+            // all destinations of one source node are distinct, so it needs no atomics.
+            Region whole{&nd, nd.n, split, 0, nd.m, 0, nd.n, st.node, 1};
+            if (excl_ok && split > nd.n && count_tiles(whole, 128, A.tile_n) >= excl_min) {
+              excl_regions.push_back(whole);
+            } else if (split > nd.n) add_tiles(A, ts, tl, nd, nd.n, split, 0, nd.m, 0, nd.n, st.node, tile_l_min);
             if (split < nd.m) {
               regions_bg.push_back({&nd, split, nd.m, 0, nd.m, 0, nd.n, st.node});
               bg_deadline = std::min(bg_deadline, dl);
@@ -560,6 +572,16 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
       }
       A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0, 0, 0});
       flush_tiles(d, 4);
+      for (const Region& r : excl_regions) {   // one launch per big finishing node, after the shared ones
+        emit_tiles(A, tl, r, 128, A.tile_n);
+        std::stable_sort(tl.begin(), tl.end(), [](const TileTask& a, const TileTask& b) {
+          return (i64)a.kk * a.mt * a.nt > (i64)b.kk * b.mt * b.nt;
+        });
+        A.launches.push_back({L_TILE_L, d, (i64)A.tile_tasks.size(), (i64)tl.size(), phase, 6, 0, 0});
+        A.tile_tasks.insert(A.tile_tasks.end(), tl.begin(), tl.end());
+        tl.clear();
+      }
+      excl_regions.clear();
       if (!regions_bg.empty()) {
         flush_tiles(d, 5, 1, bg_deadline);
         bg_deadline = 1 << 30;

@@ -155,10 +155,11 @@ void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
     case L_TILE_L:
       if (use_tma && background && A->tile_n == 64)
         launch_tiles_tma_bg(d_tile + L.begin, L.count, arena, mp, d_tmaps, d_tmaps_b, st);
-      else if (use_tma)   // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
+      else if (use_tma) {  // d_counters[i] belongs to launch i and is zeroed at the start of every factorization
+        if (getenv("SPLLT_B200_DEBUG_NOEPI")) mp.rowpos = nullptr;
         launch_tiles_tma(d_tile + L.begin, L.count, d_counters + (&L - A->launches.data()), arena, mp, d_tmaps,
                          d_tmaps_b, A->tile_n, st);
-      else
+      } else
         launch_tiles(d_tile + L.begin, L.count, true, arena, mp, st);
       break;
   }

@@ -449,7 +449,7 @@ constexpr int TM_BOXK = 16;                              // doubles per box row 
 constexpr int TM_BOX = 128 * TM_BOXK;                    // doubles per A box (16 KB)
 // stage = A lo, A hi (128 rows each) + B lo, B hi (BN rows each), KC = 32
 __host__ __device__ constexpr int tm_stage(int bn) { return 2 * TM_BOX + 2 * bn * TM_BOXK; }
-__host__ __device__ constexpr int tm_smem(int bn, int nst) { return nst * tm_stage(bn) * 8 + 1024 + 256; }
+__host__ __device__ constexpr int tm_smem(int bn, int nst) { return nst * tm_stage(bn) * 8 + 1024 + 512; }
 constexpr int SMEM_TILE_BG = 116 * 1024;   // > 227 KB / 2: one background CTA per SM
 static_assert(KC == 2 * TM_BOXK, "stage = two boxes per operand");
 
@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
   unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + TM_ST * TM_STAGE);
   unsigned long long* empty = full + TM_ST;
   StageHdr* hdr = reinterpret_cast<StageHdr*>(empty + TM_ST);
+  TileTask* ttab = reinterpret_cast<TileTask*>(hdr + TM_ST);   // task of the tile a stage belongs to
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < TM_ST; ++s) {
@@ -531,6 +532,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
         if (it >= TM_ST) mbar_wait(empty + s, ((it / TM_ST) - 1) & 1);
         if (lane == 0) {
           hdr[s] = StageHdr{ti, ch, ch == nch - 1, min(KC, t.kk - ch * KC)};
+          if (ch == 0) ttab[s] = t;
           mbar_expect_tx(full + s, TM_STAGE * 8);
           double* st = sm + s * TM_STAGE;
           int kc = t.k0 + ch * KC;
@@ -556,22 +558,24 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
   // this lane's accumulator rows are 8 i + sg(rho), its two columns 8 j + sg(2 lk + e)
   auto sg = [](int x) { return ((x & 3) << 1) | (x >> 2); };
   const int sig = sg(rho), li = sig;
-  const int cj0 = sg(2 * lk), cj1 = sg(2 * lk + 1);
   double acc[FM][FN][2];
+  TileTask t = {};
+  bool active = false;
   int it = 0;
   for (;;) {
     int s = it % TM_ST;
     mbar_wait(full + s, (it / TM_ST) & 1);
     const StageHdr h = hdr[s];
     if (h.tile < 0) break;
-    const TileTask t = tasks[h.tile];
+    // the task descriptor is handed over by the producer through shared memory, once per tile
     if (h.chunk == 0) {
+      t = ttab[s];
+      active = (t.i0 + wm0 + WM - 1 >= t.j0 + wn0) && (wm0 < t.mt) && (wn0 < t.nt);
 #pragma unroll
       for (int i = 0; i < FM; ++i)
 #pragma unroll
         for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     }
-    const bool active = (t.i0 + wm0 + WM - 1 >= t.j0 + wn0) && (wm0 < t.mt) && (wn0 < t.nt);
     if (active) {
       const double* a = sm + s * TM_STAGE + (wm0 + sig) * TM_BOXK + (lk & 1);
       const double* b = sm + s * TM_STAGE + 2 * TM_BOX + (wn0 + sig) * TM_BOXK + (lk & 1);
@@ -612,6 +616,22 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
     if (lane == 0) mbar_arrive(empty + s);
     ++it;
     if (!h.last || !active) continue;
+    if (mp.rowpos == nullptr) continue;   // timing experiment only (SPLLT_B200_DEBUG_NOEPI): no epilogue
+
+    // Lane lk holds columns {0,4,1,5}[lk] (e = 0) and {2,6,3,7}[lk] (e = 1) of each 8-column
+    // group.  One exchange between lane pairs (xor 1) re-deals them to {0,2,1,3}[lk] / {4,6,5,7}[lk],
+    // so that the four lanes of a row touch ONE 32-byte sector per store / RED instead of two.
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        double send = (lk & 1) ? acc[i][j][0] : acc[i][j][1];
+        double recv = __shfl_xor_sync(FULL, send, 1);
+        if (lk & 1) acc[i][j][0] = recv;
+        else acc[i][j][1] = recv;
+      }
+    const int cj0 = (lk & 1) ? sg(2 * (lk ^ 1) + 1) : sg(2 * lk);
+    const int cj1 = (lk & 1) ? sg(2 * lk + 1) : sg(2 * (lk ^ 1));
 
     // epilogue (see k_tile): all loads of a batch before its stores / atomics
     if (t.src < 0) {
@@ -657,23 +677,81 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
           qr[j][e] = mp.q_rp[q];
           ql[j][e] = mp.q_ld[q];
         }
+      // Destination rows: rowpos depends on (ancestor segment of the column, source row).  When
+      // all 8 columns of this thread land in the same ancestor (the common case) one index per
+      // accumulator row suffices: the 8 loads are issued together (one L2 round trip instead of
+      // one per row block), then the 64 atomics go out back to back.
+      bool same = true;
 #pragma unroll
-      for (int i = 0; i < FM; ++i) {
-        int ii = wm0 + i * 8 + li, gi = t.i0 + min(ii, t.mt - 1);
-        int rp[FN][2];
+      for (int j = 0; j < FN; ++j)
 #pragma unroll
-        for (int j = 0; j < FN; ++j)
+        for (int e = 0; e < 2; ++e) same = same && (qr[j][e] == qr[0][0]);
+      if (t.pad & 1) {
+        // Exclusive launch: every tile of this launch comes from ONE source node, so no two
+        // CTAs touch the same destination entry -> plain read-modify-write instead of RED.
+        // (Measured: the RED epilogues of a 64^3 factorization sustain ~180 G FP64 atomics/s,
+        // which is what the L2 atomic units deliver, and cost 28 % of the tile kernel's time.)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
-            bool ok = ii < t.mt && jj < t.nt && gi >= gj;
-            rp[j][e] = ok ? mp.rowpos[qr[j][e] + gi] : -1;
-          }
+        for (int i = 0; i < FM; ++i) {
+          int ii = wm0 + i * 8 + li, gi = t.i0 + min(ii, t.mt - 1);
+          double* dst[FN][2];
+          double cv[FN][2];
 #pragma unroll
-        for (int j = 0; j < FN; ++j)
+          for (int j = 0; j < FN; ++j)
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-            if (rp[j][e] >= 0) atomicAdd(arena + qb[j][e] + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+            for (int e = 0; e < 2; ++e) {
+              int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
+              bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+              dst[j][e] = ok ? arena + qb[j][e] + (i64)mp.rowpos[qr[j][e] + gi] * ql[j][e] : nullptr;
+            }
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) cv[j][e] = dst[j][e] ? *dst[j][e] : 0.0;
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (dst[j][e]) *dst[j][e] = cv[j][e] - acc[i][j][e];
+        }
+      } else if (__all_sync(FULL, same)) {
+        int rp1[FM];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) {
+          int ii = wm0 + i * 8 + li, gi = t.i0 + min(ii, t.mt - 1);
+          rp1[i] = mp.rowpos[qr[0][0] + gi];
+        }
+#pragma unroll
+        for (int i = 0; i < FM; ++i) {
+          int ii = wm0 + i * 8 + li, gi = t.i0 + ii;
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
+              if (ii < t.mt && jj < t.nt && gi >= gj)
+                atomicAdd(arena + qb[j][e] + (i64)rp1[i] * ql[j][e], -acc[i][j][e]);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < FM; ++i) {
+          int ii = wm0 + i * 8 + li, gi = t.i0 + min(ii, t.mt - 1);
+          int rp[FN][2];
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
+              bool ok = ii < t.mt && jj < t.nt && gi >= gj;
+              rp[j][e] = ok ? mp.rowpos[qr[j][e] + gi] : -1;
+            }
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (rp[j][e] >= 0) atomicAdd(arena + qb[j][e] + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+        }
       }
     }
   }
