@@ -100,6 +100,16 @@ void spllt_b200_partition_host(void *akeep, int rank, int world);
 void spllt_b200_panel_coverage(void *akeep, long long *out);
 /* [begin, end) offsets (doubles) of the shared top-of-tree region in the arena */
 void spllt_b200_shared_region(void *akeep, long long *begin, long long *end);
+/* distributed upper tree: launch records (8 columns: kind depth begin count phase tag stream
+ * deadline; kind 3 = exchange point: begin = node (0-based), count = block column, tag = owner),
+ * ranges of them run by the caller, block-column pack / unpack around its broadcasts */
+long long spllt_b200_num_launch_records(void *akeep);
+void spllt_b200_get_launch_records(void *akeep, long long *out);
+void spllt_b200_run_launches(void *fkeep, long long first, long long last);
+void spllt_b200_bcol_region(void *akeep, int node, int c, long long *off, int *ld, int *rows, int *cols);
+void spllt_b200_pack_bcol(void *akeep, void *fkeep, int node, int c, double *d_buf);
+void spllt_b200_unpack_bcol(void *akeep, void *fkeep, int node, int c, const double *d_buf);
+int spllt_b200_dist_top(void *akeep);
 /* phase 0 = assemble + local subtrees, phase 1 = shared top; both asynchronous */
 void spllt_b200_factor_phase(void *akeep, void *fkeep, const double *d_val, int phase);
 

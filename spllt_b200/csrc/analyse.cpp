@@ -504,6 +504,14 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         for (int p = 0; p * IB < w; ++p) at[t++].push_back({s, c, p});
       }
     }
+    // Distributed upper tree (multi-GPU, phase 1): every rank walks the same slots but only
+    // factorizes the block columns it owns and only computes the updates whose destination
+    // block column it owns; a finished block column is broadcast by its owner (L_EXCHANGE)
+    // before anybody uses it as a source.  No reductions are needed.
+    const bool dtop = phase == 1 && A.world > 1 && A.dist_top;
+    auto bowner = [&](int node, int c) { return A.bcol_owner[A.nodes[node].bcol0 + c]; };
+    std::vector<Region> regions_post;
+    std::vector<std::pair<int, int>> exchanges;
     for (int d = 0; d < nslots; ++d) {
       if (at[d].empty()) continue;
       i64 p0 = A.panel_tasks.size();
@@ -513,29 +521,51 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         int w = std::min(nb, nd.n - r0);
         int pw = std::min(IB, w - st.p * IB);
         int k0 = r0 + st.p * IB;
-        PanelTask pt;
-        pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
-        pt.ld = nd.ld;
-        pt.pw = pw;
-        pt.col0 = nd.sa + k0;
-        pt.pad = 0;
-        int r = k0 + pw;
-        size_t g0 = A.panel_tasks.size();
-        pt.group = A.npanel_groups++;
-        do {
-          pt.r_off = nd.off + (i64)r * nd.ld + k0;
-          pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
-          pt.store = 0;
-          A.panel_tasks.push_back(pt);
-          r += TRSM_ROWS;
-        } while (r < nd.m);
-        A.panel_tasks.back().store = 1;
-        for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
         const bool last_in_bcol = k0 + pw >= r0 + w;
-        if (!last_in_bcol) {
+        const bool own_bc = !dtop || bowner(st.node, st.c) == A.rank;
+        if (own_bc) {
+          PanelTask pt;
+          pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
+          pt.ld = nd.ld;
+          pt.pw = pw;
+          pt.col0 = nd.sa + k0;
+          pt.pad = 0;
+          int r = k0 + pw;
+          size_t g0 = A.panel_tasks.size();
+          pt.group = A.npanel_groups++;
+          do {
+            pt.r_off = nd.off + (i64)r * nd.ld + k0;
+            pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
+            pt.store = 0;
+            A.panel_tasks.push_back(pt);
+            r += TRSM_ROWS;
+          } while (r < nd.m);
+          A.panel_tasks.back().store = 1;
+          for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
           // a3 inside the block column: the columns right of this panel (K = pw)
-          add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
-        } else {
+          if (!last_in_bcol) add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+        }
+        if (last_in_bcol && dtop) {
+          exchanges.push_back({st.node, st.c});
+          // a3: later block columns of the node that this rank owns
+          for (int c2 = st.c + 1; c2 < nd.nc; ++c2)
+            if (bowner(st.node, c2) == A.rank)
+              regions_post.push_back({&nd, c2 * nb, std::min((c2 + 1) * nb, nd.n), 0, nd.m, r0, w, -1});
+          // a4: destination (ancestor, block column) runs that this rank owns
+          if (st.c + 1 == nd.nc && nd.m > nd.n) {
+            const int* idx = A.index.data() + nd.idx_off;
+            int r = nd.n;
+            while (r < nd.m) {
+              int a = A.col2node[idx[r]];
+              int cb = (idx[r] - A.nodes[a].sa) / nb;
+              int cend = std::min(A.nodes[a].sa + (cb + 1) * nb - 1, A.nodes[a].en);
+              int r1 = r;
+              while (r1 < nd.m && idx[r1] <= cend) ++r1;
+              if (bowner(a, cb) == A.rank) regions_post.push_back({&nd, r, r1, 0, nd.m, 0, nd.n, st.node});
+              r = r1;
+            }
+          }
+        } else if (last_in_bcol) {
           // a3: the finished block column updates the node's later block columns (K = w)
           if (st.c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
           // a4: the finished node updates its ancestors (K = n).  Only the columns that belong
@@ -570,8 +600,17 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
           }
         }
       }
-      A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0, 0, 0});
+      if ((i64)A.panel_tasks.size() > p0)
+        A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0, 0, 0});
       flush_tiles(d, 4);
+      if (dtop) {
+        for (auto& e : exchanges)
+          A.launches.push_back({L_EXCHANGE, d, (i64)e.first, (i64)e.second, phase, bowner(e.first, e.second), 0, 0});
+        exchanges.clear();
+        regions.insert(regions.end(), regions_post.begin(), regions_post.end());
+        regions_post.clear();
+        flush_tiles(d, 7);
+      }
       for (const Region& r : excl_regions) {   // one launch per big finishing node, after the shared ones
         emit_tiles(A, tl, r, 128, A.tile_n);
         std::stable_sort(tl.begin(), tl.end(), [](const TileTask& a, const TileTask& b) {
@@ -633,6 +672,16 @@ void partition_tree(Analysis& A, int rank, int world) {
     }
     for (size_t k = 0; k < cand.size(); ++k)
       for (int q = A.nodes[cand[k]].least_desc; q <= cand[k]; ++q) A.nodes[q].owner = where[k];
+  }
+  // block-column ownership: subtrees follow their node; upper-tree block columns are dealt
+  // cyclically (owner computes: panels, and every update whose DESTINATION it is)
+  A.dist_top = (world > 1 && !getenv("SPLLT_B200_REPLICATED_TOP")) ? 1 : 0;
+  A.bcol_owner.assign(A.nbcol, 0);
+  {
+    int next = 0;
+    for (int s = 0; s < nn; ++s)
+      for (int c = 0; c < A.nodes[s].nc; ++c)
+        A.bcol_owner[A.nodes[s].bcol0 + c] = (A.nodes[s].owner >= 0 || world <= 1) ? std::max(A.nodes[s].owner, 0) : (next++ % world);
   }
   // arena layout: owned subtrees first, shared nodes last
   i64 off = 0;

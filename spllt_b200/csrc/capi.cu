@@ -504,7 +504,8 @@ long long spllt_b200_solve_launches(void* fkeep, int job) {
 double spllt_b200_tile_flops(void* akeep) { return AA(akeep)->tile_flops; }
 void spllt_b200_launch_breakdown(void* akeep, long long* out4) {
   out4[0] = out4[1] = out4[2] = out4[3] = 0;
-  for (const Launch& L : AA(akeep)->launches) out4[L.kind]++;
+  for (const Launch& L : AA(akeep)->launches)
+    if (L.kind < 3) out4[L.kind]++;
   out4[3] = (long long)AA(akeep)->launches.size();
 }
 
@@ -554,6 +555,48 @@ void spllt_b200_panel_coverage(void* akeep, long long* out) {
   for (const PanelTask& t : A.panel_tasks)
     if (t.store) out[A.col2node[t.col0]]++;
 }
+// ---- multi-GPU stepping (distributed upper tree): the caller walks the launch records of
+// phase 1, runs the kernel ranges itself and performs the block-column broadcasts in between.
+long long spllt_b200_num_launch_records(void* akeep) { return (long long)AA(akeep)->launches.size(); }
+// 8 columns per record: kind depth begin count phase tag stream deadline
+void spllt_b200_get_launch_records(void* akeep, long long* out) {
+  const Analysis& A = *AA(akeep);
+  for (size_t i = 0; i < A.launches.size(); ++i) {
+    const Launch& L = A.launches[i];
+    long long* r = out + 8 * i;
+    r[0] = L.kind; r[1] = L.depth; r[2] = L.begin; r[3] = L.count; r[4] = L.phase; r[5] = L.tag; r[6] = L.stream;
+    r[7] = L.deadline;
+  }
+}
+void spllt_b200_run_launches(void* fkeep, long long first, long long last) {
+  Engine* e = EE(fkeep);
+  e->upload_tables();
+  for (long long i = first; i < last; ++i) e->launch_one(e->A->launches[i], e->stream, false);
+}
+// block column c (0-based) of node (1-based): arena offset, leading dimension, rows, columns
+void spllt_b200_bcol_region(void* akeep, int node, int c, long long* off, int* ld, int* rows, int* cols) {
+  const Analysis& A = *AA(akeep);
+  const HNode& nd = A.nodes[node - 1];
+  int r0 = c * A.nb;
+  *off = nd.off + (i64)r0 * nd.ld + r0;
+  *ld = nd.ld;
+  *rows = nd.m - r0;
+  *cols = std::min(A.nb, nd.n - r0);
+}
+void spllt_b200_pack_bcol(void* akeep, void* fkeep, int node, int c, double* d_buf) {
+  long long off; int ld, rows, cols;
+  spllt_b200_bcol_region(akeep, node, c, &off, &ld, &rows, &cols);
+  Engine* e = EE(fkeep);
+  launch_pack(e->arena + off, ld, rows, cols, d_buf, e->stream);
+}
+void spllt_b200_unpack_bcol(void* akeep, void* fkeep, int node, int c, const double* d_buf) {
+  long long off; int ld, rows, cols;
+  spllt_b200_bcol_region(akeep, node, c, &off, &ld, &rows, &cols);
+  Engine* e = EE(fkeep);
+  launch_unpack(e->arena + off, ld, rows, cols, d_buf, e->stream);
+}
+int spllt_b200_dist_top(void* akeep) { return AA(akeep)->dist_top; }
+
 void spllt_b200_factor_phase(void* akeep, void* fkeep, const double* d_val, int phase) {
   (void)akeep;
   Engine* e = EE(fkeep);

@@ -151,6 +151,7 @@ void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
   DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
   switch (L.kind) {
     case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, d_counters + A->launches.size(), st); break;
+    case L_EXCHANGE: break;   // not a kernel: driven by the multi-GPU caller (spllt_b200/dist.py)
     case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
     case L_TILE_L:
       if (use_tma && background && A->tile_n == 64)
@@ -320,6 +321,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   for (size_t i = 0; i < S.launches.size(); ++i) {
     const Launch& L = S.launches[i];
     CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]));
+    if (L.kind == L_EXCHANGE) continue;
     ms4[1 + L.kind] += ms;
     if (f) {
       double fl = 0;

@@ -1138,6 +1138,26 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_bwd_diag(const SolveBcol* __re
   }
 }
 
+// ------------------------------------------------------------------------------ block-column pack / unpack
+// Multi-GPU exchange of one finished block column (rows x cols sub-matrix of a node, leading
+// dimension ld) through a contiguous staging buffer.
+__global__ void k_pack(const double* __restrict__ src, int ld, int rows, int cols, double* __restrict__ dst) {
+  i64 n = (i64)rows * cols;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    i64 r = i / cols;
+    int c = (int)(i - r * cols);
+    dst[i] = src[r * ld + c];
+  }
+}
+__global__ void k_unpack(double* __restrict__ dst, int ld, int rows, int cols, const double* __restrict__ src) {
+  i64 n = (i64)rows * cols;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    i64 r = i / cols;
+    int c = (int)(i - r * cols);
+    dst[r * ld + c] = src[i];
+  }
+}
+
 // ------------------------------------------------------------------------------ launchers
 constexpr int SMEM_TILE_S = 2 * (64 + 64) * SLD * 8;
 constexpr int SMEM_TILE_L = 3 * (128 + 128) * SLD * 8;
@@ -1209,6 +1229,15 @@ void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, D
     k_tile<128, 128, 64, 32, 3><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
   else
     k_tile<64, 64, 32, 32, 2><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
+}
+
+void launch_pack(const double* src, int ld, int rows, int cols, double* dst, cudaStream_t st) {
+  i64 n = (i64)rows * cols;
+  if (n > 0) k_pack<<<(unsigned)std::min<i64>((n + 255) / 256, 148 * 8), 256, 0, st>>>(src, ld, rows, cols, dst);
+}
+void launch_unpack(double* dst, int ld, int rows, int cols, const double* src, cudaStream_t st) {
+  i64 n = (i64)rows * cols;
+  if (n > 0) k_unpack<<<(unsigned)std::min<i64>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dst, ld, rows, cols, src);
 }
 
 void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st) {

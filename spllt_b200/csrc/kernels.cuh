@@ -29,6 +29,9 @@ void launch_tiles_tma_bg(const TileTask* tasks, i64 count, double* arena, DevMap
 void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
                       const void* tmaps, const void* tmaps_b, int bn, cudaStream_t st);
 
+void launch_pack(const double* src, int ld, int rows, int cols, double* dst, cudaStream_t st);
+void launch_unpack(double* dst, int ld, int rows, int cols, const double* src, cudaStream_t st);
+
 // solve
 void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st);
 void launch_permute_out(double* x, int ldx, const int* porder, const double* xw, int n, int nrhs, cudaStream_t st);

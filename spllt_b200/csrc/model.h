@@ -80,7 +80,9 @@ struct TileTask {
   int node, pad;     // source node (selects its TMA tensor map)
 };
 
-enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_NKIND = 3 };
+// L_EXCHANGE is not a kernel: it marks where the owner of a finished upper-tree block column
+// broadcasts it to the other ranks (begin = node, count = local block column, tag = owner rank)
+enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_EXCHANGE = 3, L_NKIND = 4 };
 struct Launch {
   int kind;
   int depth;
@@ -122,6 +124,8 @@ struct Analysis {
   int n = 0, nb = 0, nemin = 32, ncpu = 1, prune = 1, min_width_blas = 8;
   int rank = 0, world = 1;   // multi-GPU partition (partition_tree)
   int tile_n = 128;          // N extent of the large tiles: 128 (one CTA/SM) or 64 (two CTAs/SM)
+  int dist_top = 0;          // multi-GPU: upper tree distributed block-column-cyclically (owner computes)
+  std::vector<int> bcol_owner;  // [nbcol] rank that factorizes / receives the updates of a block column
   i64 nnz = 0;               // entries of the user's lower triangle
   Symbolic sym;
   std::vector<int> porder;   // porder[p] = variable at pivot position p (0-based both)

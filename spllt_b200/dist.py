@@ -2,12 +2,14 @@
 
 world == 1: a thin pass-through to the C ABI.
 
-world > 1: the pruned subtrees of the assembly tree (the reference's own unit of
-tree parallelism, spllt_prune_tree with nth = number of GPUs) are dealt to ranks by weight; each
-rank factorizes its subtrees in its own HBM and accumulates their inter-node updates into its
-private copy of the upper tree; ONE exchange step -- a sum all-reduce of the contiguous
-upper-tree slice of the arena over NVLink -- hands every rank the assembled upper tree, which
-is then factorized (round 1: replicated on every rank; 2-D block-cyclic is the next step).
+world > 1: subtrees of the assembly tree are dealt to ranks by proportional
+mapping; each rank factorizes its subtrees in its own HBM and accumulates their inter-node
+updates into its private copy of the upper tree; a sum all-reduce of the contiguous upper-tree
+slice of the arena over NVLink hands every rank the assembled upper tree.  The upper tree is then
+factorized block-column-cyclically, owner computes: a rank factorizes the block columns it owns
+and computes every update whose DESTINATION block column it owns; each finished block column is
+broadcast once by its owner (NCCL) before anybody uses it as a source.  No reductions in the
+upper tree.  (SPLLT_B200_REPLICATED_TOP=1: every rank factorizes the whole upper tree instead.)
 """
 import ctypes as C
 
@@ -29,6 +31,8 @@ class DistSpLLT:
         self.local = SpLLT(nb=nb, ncpu=max(world, 1), **options)
         self.stream = stream
         self.top = None
+        self.dist_top = False
+        self.program = []
 
     # -------------------------------------------------------------- phases
     def analyse(self, n, ptr, row):
@@ -47,7 +51,40 @@ class DistSpLLT:
             base = L.spllt_b200_arena_ptr(s.fkeep)
             if e.value > b.value:
                 self.top = torch.as_tensor(_DevArray(base + 8 * b.value, e.value - b.value), device="cuda")
+            self.dist_top = bool(L.spllt_b200_dist_top(s.akeep))
+            if self.dist_top:
+                self._build_program(base)
         return flag
+
+    def _build_program(self, arena_base):
+        """Phase-1 program: runs of kernel launches separated by block-column broadcasts."""
+        import torch
+        s, L = self.local, self.local.L
+        nrec = L.spllt_b200_num_launch_records(s.akeep)
+        rec = np.zeros((max(nrec, 1), 8), dtype=np.int64)
+        L.spllt_b200_get_launch_records(s.akeep, rec.ctypes.data_as(C.POINTER(C.c_longlong)))
+        rec = rec[:nrec]
+        self.program = []
+        run_start = None
+        maxbuf = 0
+        off, ld, rows, cols = C.c_longlong(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        for i in range(nrec):
+            kind, phase = int(rec[i, 0]), int(rec[i, 4])
+            if phase != 1:
+                continue
+            if kind == 3:
+                if run_start is not None:
+                    self.program.append(("run", run_start, i))
+                    run_start = None
+                node, c, owner = int(rec[i, 2]), int(rec[i, 3]), int(rec[i, 5])
+                L.spllt_b200_bcol_region(s.akeep, node + 1, c, C.byref(off), C.byref(ld), C.byref(rows), C.byref(cols))
+                self.program.append(("bcast", node + 1, c, owner, rows.value * cols.value))
+                maxbuf = max(maxbuf, rows.value * cols.value)
+            elif run_start is None:
+                run_start = i
+        if run_start is not None:
+            self.program.append(("run", run_start, nrec))
+        self.staging = torch.empty(max(maxbuf, 1), dtype=torch.float64, device="cuda")
 
     def factor_dev(self, d_val):
         """d_val: torch CUDA tensor holding the user's val.  Asynchronous on the stream."""
@@ -56,10 +93,24 @@ class DistSpLLT:
             s.factor_dev(d_val.data_ptr())
             return
         import torch.distributed as dist
-        s.L.spllt_b200_factor_phase(s.akeep, s.fkeep, C.c_void_p(d_val.data_ptr()), 0)
+        L = s.L
+        L.spllt_b200_factor_phase(s.akeep, s.fkeep, C.c_void_p(d_val.data_ptr()), 0)
         if self.top is not None:
             dist.all_reduce(self.top, op=dist.ReduceOp.SUM)     # the exchange step (NCCL over NVLink)
-        s.L.spllt_b200_factor_phase(s.akeep, s.fkeep, C.c_void_p(d_val.data_ptr()), 1)
+        if not self.dist_top:
+            L.spllt_b200_factor_phase(s.akeep, s.fkeep, C.c_void_p(d_val.data_ptr()), 1)
+            return
+        for op in self.program:
+            if op[0] == "run":
+                L.spllt_b200_run_launches(s.fkeep, op[1], op[2])
+            else:
+                _, node, c, owner, count = op
+                buf = self.staging[:count]
+                if owner == self.rank:
+                    L.spllt_b200_pack_bcol(s.akeep, s.fkeep, node, c, C.c_void_p(buf.data_ptr()))
+                dist.broadcast(buf, src=owner)
+                if owner != self.rank:
+                    L.spllt_b200_unpack_bcol(s.akeep, s.fkeep, node, c, C.c_void_p(buf.data_ptr()))
 
     def factor_host(self, val):
         """Reference-facing call with a HOST val array (spllt_factor)."""
@@ -109,7 +160,9 @@ class DistSpLLT:
         top = float(per[own < 0].sum())
         mine = float(per[own == self.rank].sum())
         nsub = int(np.sum((own >= 0) & ((par >= s.nnodes) | (own[np.minimum(par, s.nnodes - 1)] < 0))))
+        how = ("distributed block-column-cyclically (owner computes, %d block-column broadcasts)"
+               % sum(1 for op in self.program if op[0] == "bcast")) if self.dist_top else "replicated"
         return ("subtree->GPU proportional mapping (%d subtrees), sum all-reduce of the %.2f GB upper-tree "
-                "slice, upper tree (%.0f%% of flops) replicated; rank %d subtree share %.1f%%"
-                % (nsub, (self.top_range[1] - self.top_range[0]) * 8 / 1e9, 100 * top / tot, self.rank,
+                "slice, upper tree (%.0f%% of flops) %s; rank %d subtree share %.1f%%"
+                % (nsub, (self.top_range[1] - self.top_range[0]) * 8 / 1e9, 100 * top / tot, how, self.rank,
                    100 * mine / tot))

@@ -85,8 +85,19 @@ def main():
     nodes = s.nodes()
     npanels = np.array([sum(-(-min(nb, int(nodes[k, 1] - nodes[k, 0] + 1) - c0) // 64)
                             for c0 in range(0, int(nodes[k, 1] - nodes[k, 0] + 1), nb)) for k in range(nn)])
-    assert np.array_equal(cnt[mine], npanels[mine]), "a block column of this rank is missing / duplicated"
-    assert np.all(cnt[~mine] == 0), "this rank schedules work on a foreign subtree"
+    assert np.array_equal(cnt[own == rank], npanels[own == rank]), "a block column of this rank is missing / duplicated"
+    assert np.all(cnt[(own >= 0) & (own != rank)] == 0), "this rank schedules work on a foreign subtree"
+    # upper tree: replicated -> every rank holds every panel; distributed -> every panel exactly once overall
+    tsum = torch.from_numpy(cnt.copy())
+    if not cpu:
+        tsum = tsum.cuda()
+    dist.all_reduce(tsum)
+    tsum = tsum.cpu().numpy()
+    top = own == -1
+    if s.L.spllt_b200_dist_top(s.akeep):
+        assert np.array_equal(tsum[top], npanels[top]), "an upper-tree panel is missing / duplicated across ranks"
+    else:
+        assert np.array_equal(cnt[top], npanels[top])
     if cpu:
         dist.barrier()
         if rank == 0:
