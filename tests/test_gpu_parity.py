@@ -292,3 +292,25 @@ def test_elasticity_config_small():
     s.prepare_solve(2)
     s.solve(x, 0)
     assert chkerr(n, ptr, row, val, x, b)[0] == 2
+
+
+@pytest.mark.parametrize("env", [
+    {"SPLLT_B200_GRAPH": "0"},
+    {"SPLLT_B200_NO_OVERLAP": "1"},
+    {"SPLLT_B200_TILE_N": "128", "SPLLT_B200_TILE_WAVE": "1", "SPLLT_B200_TILE_L_MIN": "32"},
+    {"SPLLT_B200_DEFER": "1", "SPLLT_B200_TILE_WAVE": "1", "SPLLT_B200_TILE_L_MIN": "32"},
+    {"SPLLT_B200_EXCL": "1", "SPLLT_B200_EXCL_MIN": "1", "SPLLT_B200_TILE_WAVE": "1", "SPLLT_B200_TILE_L_MIN": "32"},
+], ids=["nograph", "nooverlap", "tile128", "deferred-bg-stream", "exclusive-no-atomics"])
+@pytest.mark.parametrize("case", [SMALL[11], MEDIUM[1]], ids=ids([SMALL[11], MEDIUM[1]]))
+def test_schedule_variants(case, env, monkeypatch):
+    """Every opt-in / fallback execution mode of the factorization schedule produces the same factor."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    s, o, mat = both(case)
+    assert_factor_close(s.factor_entries(), o.factor_entries(), lower_mask(s))
+    n, ptr, row, val = mat
+    xs, b = rhs_for(mat, 2)
+    x = b.copy(order="F")
+    s.prepare_solve(2)
+    s.solve(x, 0)
+    assert chkerr(n, ptr, row, val, x, b)[0] == 2

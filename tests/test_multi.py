@@ -26,10 +26,14 @@ def test_partition_gloo_cpu(world, grid, nb):
 
 
 @pytest.mark.gpu
-def test_distributed_factor_nccl():
+@pytest.mark.parametrize("replicated", ["0", "1"], ids=["distributed-top", "replicated-top"])
+def test_distributed_factor_nccl(replicated):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    r = run_ranks(2, {"SPLLT_DIST_GRID": "24", "SPLLT_DIST_NB": "64"}, 29531)
+    env = {"SPLLT_DIST_GRID": "24", "SPLLT_DIST_NB": "64"}
+    if replicated == "1":
+        env["SPLLT_B200_REPLICATED_TOP"] = "1"
+    r = run_ranks(2, env, 29531 + int(replicated))
     assert r.returncode == 0, r.stdout[-3000:]
     assert "dist_check gpu ok" in r.stdout
