@@ -94,3 +94,20 @@ def test_matrix_market_reader(tmp_path):
     scipy.io.mmwrite(str(p), sps.coo_matrix(a), symmetry="symmetric")
     n2, ptr2, row2, val2 = read_matrix_market(str(p))
     assert n2 == n and np.array_equal(ptr2, ptr) and np.array_equal(row2, row) and np.allclose(val2, val)
+
+
+def test_empty_matrix_and_unsorted_rows():
+    s = sp.SpLLT(nb=8)
+    assert s.analyse(0, np.array([1], np.int32), np.array([], np.int32)) == 0
+    assert s.nnodes == 0 and s.num_flops == 0 and s.prepare_solve_size(2) == 0
+    # row indices need not be sorted inside a column (the reference goes through spllt_make_map)
+    n, ptr, row, val = M.poisson2d(6)
+    rng = np.random.default_rng(0)
+    row2 = row.copy()
+    for j in range(n):
+        a, b = ptr[j] - 1, ptr[j + 1] - 1
+        row2[a:b] = row[a:b][rng.permutation(b - a)]
+    s1, s2 = sp.SpLLT(nb=8), sp.SpLLT(nb=8)
+    s1.analyse(n, ptr, row)
+    s2.analyse(n, ptr, row2)
+    assert np.array_equal(s1.order, s2.order) and np.array_equal(s1.blocks(), s2.blocks())

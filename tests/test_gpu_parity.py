@@ -314,3 +314,28 @@ def test_schedule_variants(case, env, monkeypatch):
     s.prepare_solve(2)
     s.solve(x, 0)
     assert chkerr(n, ptr, row, val, x, b)[0] == 2
+
+
+def test_unsorted_input_columns():
+    """Entries of a column may come in any order; the A -> L map follows the input order."""
+    n, ptr, row, val = M.poisson3d(8)
+    rng = np.random.default_rng(1)
+    row2, val2 = row.copy(), val * (1.0 + 0.01 * rng.standard_normal(val.size))
+    diag = row == np.repeat(np.arange(1, n + 1), np.diff(ptr))
+    val2[diag] = np.abs(val2[diag]) + 1.0
+    val3 = val2.copy()
+    for j in range(n):
+        a, b = ptr[j] - 1, ptr[j + 1] - 1
+        p = rng.permutation(b - a)
+        row2[a:b], val3[a:b] = row[a:b][p], val2[a:b][p]
+    xs = np.ones(n)
+    bvec = M.matvec(n, ptr, row, val2, xs)
+    for r_, v_ in ((row, val2), (row2, val3)):
+        s = sp.SpLLT(nb=16)
+        s.analyse(n, ptr, r_)
+        s.factor(v_)
+        s.wait()
+        x = bvec.copy()
+        s.prepare_solve(1)
+        s.solve(x, 0)
+        assert chkerr(n, ptr, row, val2, x, bvec)[0] == 1
