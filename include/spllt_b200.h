@@ -80,8 +80,17 @@ void spllt_b200_launch_breakdown(void *akeep, long long *out4);
  * one line per launch.  Synchronises. */
 void spllt_b200_profile_factor(void *fkeep, const double *d_val, double *ms4, const char *csv);
 
-/* same for one forward + backward solve: ms4 = {fwd_diag, fwd_upd, bwd_upd, bwd_diag} */
-void spllt_b200_profile_solve(void *fkeep, int nrhs, double *d_x, int ldx, double *ms4, const char *csv);
+/* same for one forward + backward solve: ms6 = {fwd_diag, fwd_upd, bwd_upd, bwd_diag (level-set
+ * launches, only used below SPLLT_B200_SOLVE_CUT), fwd_pipe, bwd_pipe (persistent kernels)} */
+void spllt_b200_profile_solve(void *fkeep, int nrhs, double *d_x, int ldx, double *ms6, const char *csv);
+
+/* pipelined-solve work lists (value independent; tests replay them to prove the claim order is
+ * deadlock free).  sizes: out4 = {forward tasks, backward tasks, strips, dest entries};
+ * tasks: 6 ints each {node (0-based), kind (0 diag strip, 1 below chunk, 2 fused small node), r0,
+ * nrows, dest_begin, dest_count}; nodes: 8 ints each {m, n, sa, strip0, np, expect_f, expect_b,
+ * pflag}; dest: node ids */
+void spllt_b200_pipe_sizes(void *akeep, long long *out4);
+void spllt_b200_get_pipe(void *akeep, int *tasks_f, int *tasks_b, int *nodes, int *dest);
 
 /* ---- FP64 peak probes (no FP64 figure in MEASURED_PEAKS.json): enqueue a register-resident
  * DMMA (kind 0) or DFMA (kind 1) loop on every SM; returns the flops it will execute */

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspllt_b200.so")
-SOURCES = ["kernels.cu", "engine.cu", "capi.cu", "analyse.cpp", "symbolic.cpp"]
+SOURCES = ["kernels.cu", "solve_pipe.cu", "engine.cu", "capi.cu", "analyse.cpp", "symbolic.cpp"]
 HEADERS = ["kernels.cuh", "engine.h", "model.h", "symbolic.h",
            os.path.join("..", "..", "include", "spllt_iface.h"),
            os.path.join("..", "..", "include", "spllt_b200.h")]

@@ -701,14 +701,104 @@ void partition_tree(Analysis& A, int rank, int world) {
 // ------------------------------------------------------------------------------------------
 // Solve schedule: the same block-column level sets.  Forward: diag solve of the block
 // column, then x[index[r]] -= L[r, bcol] * x_bcol for the rows below.  Backward: the reverse.
+static void build_pipe_schedule(Analysis& A) {
+  // Persistent-kernel solve: tasks in a topological order of the assembly tree, (depth0, node)
+  // ascending for the forward sweep, the reverse for the backward sweep.  A task only ever
+  // waits on tasks that precede it in its list, so claiming tasks in list order from running
+  // CTAs cannot deadlock (tests/test_symbolic.py replays the lists and checks exactly that).
+  const int nn = A.nnodes, cut = A.solve_cut;
+  A.pnodes.assign(nn, PNode{});
+  A.ptasks_f.clear();
+  A.ptasks_b.clear();
+  A.pipe_dest.clear();
+  int strip = 0;
+  for (int s = 0; s < nn; ++s) {
+    const HNode& nd = A.nodes[s];
+    PNode& p = A.pnodes[s];
+    p.off = nd.off;
+    p.idx_off = nd.idx_off;
+    p.ld = nd.ld;
+    p.m = nd.m;
+    p.n = nd.n;
+    p.sa = nd.sa;
+    p.strip0 = strip;
+    p.np = (nd.n + PS - 1) / PS;
+    p.expect_f = p.expect_b = 0;
+    p.pflag = -1;
+    strip += p.np;
+  }
+  A.nstrips = strip;
+  for (int s = 0; s < nn; ++s)
+    if (A.nodes[s].parent >= 0) A.pnodes[s].pflag = A.pnodes[A.nodes[s].parent].strip0;
+  std::vector<int> ord;
+  for (int s = 0; s < nn; ++s)
+    if (A.nodes[s].depth0 >= cut) ord.push_back(s);
+  std::stable_sort(ord.begin(), ord.end(),
+                   [&](int a, int b) { return A.nodes[a].depth0 < A.nodes[b].depth0; });
+  auto dests = [&](int s, int r0, int r1, int* begin, int* count) {
+    // distinct ancestor nodes owning rows [r0, r1) of node s (index is sorted => runs)
+    *begin = (int)A.pipe_dest.size();
+    const int* idx = A.index.data() + A.nodes[s].idx_off;
+    int last = -1;
+    for (int r = r0; r < r1; ++r) {
+      int d = A.col2node[idx[r]];
+      if (d != last) {
+        A.pipe_dest.push_back(d);
+        A.pnodes[d].expect_f++;
+        last = d;
+      }
+    }
+    *count = (int)A.pipe_dest.size() - *begin;
+  };
+  auto is_small = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
+  for (int s : ord) {
+    const HNode& nd = A.nodes[s];
+    if (is_small(nd)) {
+      PTask t{s, P_SMALL, 0, 0, 0, 0, {0, 0}};
+      dests(s, nd.n, nd.m, &t.dest_begin, &t.dest_count);
+      A.ptasks_f.push_back(t);
+      continue;
+    }
+    for (int i = 0; i < A.pnodes[s].np; ++i) A.ptasks_f.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
+    for (int r = nd.n; r < nd.m; r += PS) {
+      PTask t{s, P_BELOW, r, std::min(PS, nd.m - r), 0, 0, {0, 0}};
+      dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
+      A.ptasks_f.push_back(t);
+    }
+  }
+  for (auto it = ord.rbegin(); it != ord.rend(); ++it) {
+    const int s = *it;
+    const HNode& nd = A.nodes[s];
+    if (is_small(nd)) {
+      A.ptasks_b.push_back(PTask{s, P_SMALL, 0, 0, 0, 0, {0, 0}});
+      continue;
+    }
+    for (int r = nd.n; r < nd.m; r += PS) {
+      A.ptasks_b.push_back(PTask{s, P_BELOW, r, std::min(PS, nd.m - r), 0, 0, {0, 0}});
+      A.pnodes[s].expect_b++;
+    }
+    for (int i = A.pnodes[s].np - 1; i >= 0; --i) A.ptasks_b.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
+  }
+}
+
 void build_solve_schedule(Analysis& A) {
   const int nn = A.nnodes, nb = A.nb;
+  // SPLLT_B200_SOLVE_CUT = d: nodes whose first block column sits at schedule depth < d are
+  // solved by the level-set launches, the rest by the persistent pipelined kernels.
+  // default 0 = everything pipelined; SPLLT_B200_SOLVE_LEVELSET=1 = everything level-set.
+  {
+    const char* e = getenv("SPLLT_B200_SOLVE_CUT");
+    A.solve_cut = e ? atoi(e) : 0;
+    const char* l = getenv("SPLLT_B200_SOLVE_LEVELSET");
+    if (l && atoi(l)) A.solve_cut = 1 << 30;
+  }
   A.sbcols.clear();
   A.supds.clear();
   A.slaunch.assign(A.ndepth, SolveLaunch{0, 0, 0, 0});
   std::vector<std::vector<int>> at(A.ndepth);
   for (int s = 0; s < nn; ++s)
-    for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
+    if (A.nodes[s].depth0 < A.solve_cut)
+      for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
   for (int d = 0; d < A.ndepth; ++d) {
     SolveLaunch& L = A.slaunch[d];
     L.diag_begin = A.sbcols.size();
@@ -732,6 +822,7 @@ void build_solve_schedule(Analysis& A) {
     L.diag_count = (i64)A.sbcols.size() - L.diag_begin;
     L.upd_count = (i64)A.supds.size() - L.upd_begin;
   }
+  build_pipe_schedule(A);
 }
 
 }  // namespace spllt

@@ -496,9 +496,9 @@ long long spllt_b200_solve_launches(void* fkeep, int job) {
   const Analysis& A = *EE(fkeep)->A;
   long long per = 0;
   for (const SolveLaunch& L : A.slaunch) per += (L.diag_count > 0) + (L.upd_count > 0);
-  long long tot = 0;
-  if (job == 0 || job == 1) tot += per + 1;
-  if (job == 0 || job == 2) tot += per + 1;
+  long long tot = 0;   // level-set launches (below the cut) + persistent kernel + permutation
+  if (job == 0 || job == 1) tot += per + !A.ptasks_f.empty() + 1;
+  if (job == 0 || job == 2) tot += per + !A.ptasks_b.empty() + 1;
   return tot;
 }
 double spllt_b200_tile_flops(void* akeep) { return AA(akeep)->tile_flops; }
@@ -513,10 +513,32 @@ void spllt_b200_profile_factor(void* fkeep, const double* d_val, double* ms4, co
   EE(fkeep)->profile_factor(d_val, ms4, csv);
 }
 
-void spllt_b200_profile_solve(void* fkeep, int nrhs, double* d_x, int ldx, double* ms4, const char* csv) {
-  EE(fkeep)->profile_solve(d_x, ldx, nrhs, ms4, csv);
+void spllt_b200_profile_solve(void* fkeep, int nrhs, double* d_x, int ldx, double* ms6, const char* csv) {
+  EE(fkeep)->profile_solve(d_x, ldx, nrhs, ms6, csv);
 }
 
+void spllt_b200_pipe_sizes(void* akeep, long long* out4) {
+  const Analysis& A = *AA(akeep);
+  out4[0] = (long long)A.ptasks_f.size();
+  out4[1] = (long long)A.ptasks_b.size();
+  out4[2] = A.nstrips;
+  out4[3] = (long long)A.pipe_dest.size();
+}
+void spllt_b200_get_pipe(void* akeep, int* tasks_f, int* tasks_b, int* nodes, int* dest) {
+  const Analysis& A = *AA(akeep);
+  auto put = [](const std::vector<PTask>& v, int* o) {
+    for (const PTask& t : v) {
+      *o++ = t.node; *o++ = t.kind; *o++ = t.r0; *o++ = t.nrows; *o++ = t.dest_begin; *o++ = t.dest_count;
+    }
+  };
+  put(A.ptasks_f, tasks_f);
+  put(A.ptasks_b, tasks_b);
+  for (const PNode& p : A.pnodes) {
+    *nodes++ = p.m; *nodes++ = p.n; *nodes++ = p.sa; *nodes++ = p.strip0;
+    *nodes++ = p.np; *nodes++ = p.expect_f; *nodes++ = p.expect_b; *nodes++ = p.pflag;
+  }
+  for (int d : A.pipe_dest) *dest++ = d;
+}
 double spllt_b200_peak_probe(int kind, int iters, void* stream) {
   require_gpu();
   if (kind >= 10) return launch_dmma_warps(iters, kind - 10, (cudaStream_t)stream);

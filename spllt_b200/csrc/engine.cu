@@ -49,6 +49,7 @@ void Engine::upload_tables() {
   require_gpu();
   if (!g_kernels_ready) {
     kernels_init();
+    pipe_init();
     g_kernels_ready = true;
   }
   CK(cudaGetDevice(&device));
@@ -129,6 +130,10 @@ void Engine::upload_tables() {
   }
   d_sb = upload(S.sbcols);
   d_su = upload(S.supds);
+  d_pnodes = upload(S.pnodes);
+  d_ptask_f = upload(S.ptasks_f);
+  d_ptask_b = upload(S.ptasks_b);
+  d_pdest = upload(S.pipe_dest);
   d_index = upload(S.index);
   d_porder = upload(S.porder);
   int maxw = 1;
@@ -144,6 +149,9 @@ void Engine::ensure_solve_buffers(int nrhs) {
   CK(cudaMalloc(&d_xw, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
   CK(cudaMalloc(&d_x, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
   CK(cudaMemset(d_xw, 0, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
+  if (d_psync) CK(cudaFree(d_psync));
+  psync_ints = pipe_sync_ints(A->nstrips, A->nnodes, nrhs);
+  CK(cudaMalloc(&d_psync, 2 * psync_ints * sizeof(int)));
   xw_nrhs = nrhs;
 }
 
@@ -354,8 +362,12 @@ void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
       launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
       launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
     }
+    launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs,
+                      S.nstrips, S.nnodes, d_psync, st);
   }
   if (job == 0 || job == 2) {
+    launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs,
+                      S.nstrips, S.nnodes, d_psync + psync_ints, st);
     for (int d = S.ndepth - 1; d >= 0; --d) {
       const SolveLaunch& L = S.slaunch[d];
       launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
@@ -394,54 +406,66 @@ void Engine::solve(double* dx, int ldx, int nrhs, int job) {
   if (job == 0 || job == 2) launch_permute_out(dx, ldx, d_porder, d_xw, A->n, nrhs, stream);
 }
 
-// Un-graphed forward + backward solve with one event pair per launch: ms4 = {fwd_diag, fwd_upd,
-// bwd_upd, bwd_diag}; csv (optional) gets one line per launch.  Diagnostic only.
-void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms4, const char* csv) {
+// Un-graphed forward + backward solve with one event pair per launch: ms6 = {fwd_diag, fwd_upd,
+// bwd_upd, bwd_diag, fwd_pipe, bwd_pipe}; csv (optional) gets one line per launch.  Diagnostic only.
+void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const char* csv) {
   upload_tables();
-  for (int i = 0; i < 4; ++i) ms4[i] = 0;
+  for (int i = 0; i < 6; ++i) ms6[i] = 0;
   if (A->n == 0) return;
   ensure_solve_buffers(nrhs);
   const Analysis& S = *A;
   cudaStream_t st = stream;
-  std::vector<cudaEvent_t> ev(4 * S.ndepth + 1);
-  for (auto& e : ev) CK(cudaEventCreate(&e));
+  struct Rec {
+    int kind, depth;
+    long long ctas;
+  };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> ev;
+  auto mark = [&]() {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(e, st));
+    ev.push_back(e);
+  };
   launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
-  int e = 0;
-  CK(cudaEventRecord(ev[e++], st));
+  mark();
   for (int d = 0; d < S.ndepth; ++d) {
     const SolveLaunch& L = S.slaunch[d];
+    if (L.diag_count == 0 && L.upd_count == 0) continue;
     launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
-    CK(cudaEventRecord(ev[e++], st));
+    mark();
+    recs.push_back({0, d, L.diag_count});
     launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
-    CK(cudaEventRecord(ev[e++], st));
+    mark();
+    recs.push_back({1, d, L.upd_count});
   }
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs, S.nstrips,
+                    S.nnodes, d_psync, st);
+  mark();
+  recs.push_back({4, -1, (long long)S.ptasks_f.size()});
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs,
+                    S.nstrips, S.nnodes, d_psync + psync_ints, st);
+  mark();
+  recs.push_back({5, -1, (long long)S.ptasks_b.size()});
   for (int d = S.ndepth - 1; d >= 0; --d) {
     const SolveLaunch& L = S.slaunch[d];
+    if (L.diag_count == 0 && L.upd_count == 0) continue;
     launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
-    CK(cudaEventRecord(ev[e++], st));
+    mark();
+    recs.push_back({2, d, L.upd_count});
     launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
-    CK(cudaEventRecord(ev[e++], st));
+    mark();
+    recs.push_back({3, d, L.diag_count});
   }
   launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
   CK(cudaStreamSynchronize(st));
   FILE* f = csv ? fopen(csv, "w") : nullptr;
   if (f) fprintf(f, "kind,depth,ctas,ms\n");
-  for (int i = 0; i < 4 * S.ndepth; ++i) {
+  for (size_t i = 0; i < recs.size(); ++i) {
     float ms;
     CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-    int kind, d;
-    if (i < 2 * S.ndepth) {
-      kind = i & 1;
-      d = i / 2;
-    } else {
-      int j = i - 2 * S.ndepth;
-      kind = 2 + (j & 1);
-      d = S.ndepth - 1 - j / 2;
-    }
-    ms4[kind] += ms;
-    const SolveLaunch& L = S.slaunch[d];
-    if (f)
-      fprintf(f, "%d,%d,%lld,%.6f\n", kind, d, (long long)((kind == 0 || kind == 3) ? L.diag_count : L.upd_count), ms);
+    ms6[recs[i].kind] += ms;
+    if (f) fprintf(f, "%d,%d,%lld,%.6f\n", recs[i].kind, recs[i].depth, recs[i].ctas, ms);
   }
   if (f) fclose(f);
   for (auto& x : ev) CK(cudaEventDestroy(x));
@@ -510,6 +534,12 @@ void Engine::release() {
   d_tmaps = d_tmaps_b = nullptr;
   cudaFree(d_sb);
   cudaFree(d_su);
+  cudaFree(d_pnodes);
+  cudaFree(d_ptask_f);
+  cudaFree(d_ptask_b);
+  cudaFree(d_pdest);
+  if (d_psync) cudaFree(d_psync);
+  d_psync = nullptr;
   cudaFree(d_index);
   cudaFree(d_porder);
   if (d_xw) cudaFree(d_xw);

@@ -53,6 +53,12 @@ struct Engine {
   void* d_tmaps_b = nullptr;  // same with tile_n-row boxes (B operand)
   SolveBcol* d_sb = nullptr;
   SolveUpd* d_su = nullptr;
+  PNode* d_pnodes = nullptr;      // pipelined solve tables (solve_pipe.cu)
+  PTask* d_ptask_f = nullptr;
+  PTask* d_ptask_b = nullptr;
+  int* d_pdest = nullptr;
+  int* d_psync = nullptr;         // flags + counters: forward region, then backward region
+  i64 psync_ints = 0;             // ints per region
   int* d_index = nullptr;
   int* d_porder = nullptr;
   double* d_xw = nullptr;  // pivot-order work vector, n x nrhs row-major (persists between job 1 and job 2)
@@ -77,7 +83,7 @@ struct Engine {
   void launch_one(const Launch& L, cudaStream_t st, bool background);
   void enqueue_solve(int nrhs, int job, cudaStream_t st);
   void solve(double* dx, int ldx, int nrhs, int job);
-  void profile_solve(double* dx, int ldx, int nrhs, double* ms4, const char* csv);
+  void profile_solve(double* dx, int ldx, int nrhs, double* ms6, const char* csv);
   void solve_host(double* x, int nrhs, int job);
   void sync();
   int pivot_flag();

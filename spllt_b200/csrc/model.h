@@ -112,6 +112,34 @@ struct SolveLaunch {
   i64 upd_begin, upd_count;     // SolveUpd range
 };
 
+// ------------------------------------------------------------------ pipelined solve (solve_pipe.cu)
+// The default solve: ONE persistent kernel per sweep.  CTAs claim tasks from a global counter in
+// a topological order (forward: children before parents; backward: the reverse) and synchronise
+// through flags / counters in HBM instead of kernel boundaries -- the device-resident
+// replacement of the solve task DAG (fwd_wdep / bwd_wdep, src/spllt_solve_dep_mod.F90:27-248).
+// Granularity: 64-row strips of a node's diagonal block (a13) and 64-row chunks of the rows
+// below it (a14/a15), independent of the factorization's nb.
+constexpr int PS = 64;           // strip width of the pipelined solve
+constexpr int PIPE_SMALL_ROWS = 256;  // nodes with n <= PS and m - n <= this are one fused task
+enum PipeKind { P_DIAG = 0, P_BELOW = 1, P_SMALL = 2 };
+struct PNode {
+  i64 off;           // arena offset of the node
+  i64 idx_off;       // node index list
+  int ld, m, n, sa;
+  int strip0;        // flag index of the node's first strip
+  int np;            // strips = ceil(n / PS)
+  int expect_f;      // forward: tasks of descendants that add into this node's rows
+  int expect_b;      // backward: below-chunk tasks of this node
+  int pflag;         // backward: flag index of the parent's strip 0 (-1: root)
+  int pad[3];
+};
+struct PTask {
+  int node, kind;
+  int r0, nrows;     // P_DIAG: r0 = strip index; P_BELOW: rows [r0, r0 + nrows) of the node (r0 >= n)
+  int dest_begin, dest_count;  // forward: nodes whose counters this task bumps (pipe_dest)
+  int pad[2];
+};
+
 // ------------------------------------------------------------------ reference-format tables
 struct RefBlock {    // spllt_block, 1-based (src/spllt_data_mod.F90:123-172)
   i64 id;
@@ -165,6 +193,13 @@ struct Analysis {
   std::vector<SolveBcol> sbcols;
   std::vector<SolveUpd> supds;
   std::vector<SolveLaunch> slaunch;   // one per depth
+  // pipelined solve: nodes with depth0 >= solve_cut run in the persistent kernels, the rest
+  // (none by default) in the level-set launches above
+  int solve_cut = 0;
+  int nstrips = 0;
+  std::vector<PNode> pnodes;          // [nnodes]
+  std::vector<PTask> ptasks_f, ptasks_b;
+  std::vector<int> pipe_dest;
 };
 
 // analyse.cpp

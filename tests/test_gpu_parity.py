@@ -316,6 +316,39 @@ def test_schedule_variants(case, env, monkeypatch):
     assert chkerr(n, ptr, row, val, x, b)[0] == 2
 
 
+@pytest.mark.parametrize("env", [
+    {},
+    {"SPLLT_B200_SOLVE_LEVELSET": "1"},
+    {"SPLLT_B200_SOLVE_CUT": "2"},
+    {"SPLLT_B200_SOLVE_CUT": "5", "SPLLT_B200_GRAPH": "0"},
+], ids=["pipelined", "levelset", "cut2", "cut5-nograph"])
+@pytest.mark.parametrize("case", [SMALL[7], SMALL[11], MEDIUM[1], MEDIUM[2], MEDIUM[3]],
+                         ids=ids([SMALL[7], SMALL[11], MEDIUM[1], MEDIUM[2], MEDIUM[3]]))
+@pytest.mark.parametrize("nrhs", [1, 6])
+def test_solve_variants(case, env, nrhs, monkeypatch):
+    """The persistent pipelined solve (default), the level-set launches, and hybrids of the two
+    give the oracle's solution; forward-only + backward-only equals the full solve."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    s, o, mat = both(case)
+    n, ptr, row, val = mat
+    xs, b = rhs_for(mat, nrhs, seed=3)
+    s.prepare_solve(nrhs)
+    o.prepare_solve(nrhs)
+    xo = b.copy(order="F")
+    o.solve(xo, 0)
+    for rep in range(3):          # replays of the captured graph must reset flags and counters
+        x = b.copy(order="F")
+        assert s.solve(x, 0) == 0
+        ok, err = chkerr(n, ptr, row, val, x, b)
+        assert ok == nrhs and err.max() <= BWD_TOL
+        assert np.max(np.abs(x - xo)) <= 1e-10 * np.abs(xo).max()
+    x2 = b.copy(order="F")
+    assert s.solve(x2, 1) == 0
+    assert s.solve(x2, 2) == 0
+    assert np.max(np.abs(x2 - xo)) <= 1e-10 * np.abs(xo).max()
+
+
 def test_unsorted_input_columns():
     """Entries of a column may come in any order; the A -> L map follows the input order."""
     n, ptr, row, val = M.poisson3d(8)

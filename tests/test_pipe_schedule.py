@@ -1,0 +1,187 @@
+"""Pipelined solve (spllt_b200/csrc/solve_pipe.cu): the value-independent work lists.
+
+The persistent kernels let CTAs claim tasks in list order and wait on flags / counters, so the
+lists must be topological: replaying them ONE task at a time must find every wait already
+satisfied (=> in-order claiming cannot deadlock), every counter must reach exactly its expected
+value before it is consumed, and the tasks must cover every row of every node exactly once.
+A second test replays the same lists numerically (numpy, the arithmetic each task performs, on
+the oracle's factor) and checks the solution -- the decomposition itself, independent of CUDA.
+CPU only."""
+import numpy as np
+import pytest
+
+import spllt_b200 as sp
+from oracle.oracle import Oracle, chkerr
+from spllt_b200 import matrices as M
+from tests.cases import SMALL, MEDIUM, ids
+
+PS = 64
+DIAG, BELOW, SMALLK = 0, 1, 2
+
+EXTRA = [
+    ("p3d-24-nb64", lambda: M.poisson3d(24), 64, 4, 1),
+    ("el3d-9-nb96", lambda: M.elasticity3d(9), 96, 4, 1),
+    ("rand300-dense-nb32", lambda: M.random_spd(300, 0.3, 2), 32, 2, 1),
+]
+CASES = SMALL + MEDIUM + EXTRA
+
+
+def tables(case):
+    name, mk, nb, ncpu, prune = case
+    n, ptr, row, val = mk()
+    s = sp.SpLLT(nb=nb, ncpu=ncpu, prune_tree=prune)
+    assert s.analyse(n, ptr, row) == 0
+    sptr, sparent, rptr, rlist = s.symbolic()
+    return s, (n, ptr, row, val), (sptr, sparent, rptr, rlist)
+
+
+@pytest.mark.parametrize("case", CASES, ids=ids(CASES))
+def test_lists_are_topological_and_cover(case):
+    s, (n, ptr, row, val), (sptr, sparent, rptr, rlist) = tables(case)
+    tf, tb, nd, dest, nstrips = s.pipe_tables()
+    nn = s.nnodes
+    m_, n_, sa, strip0, np_, exp_f, exp_b, pflag = nd.T
+    assert np.array_equal(n_, np.diff(sptr)) and np.array_equal(m_, np.diff(rptr))
+    assert np.array_equal(sa, sptr[:-1] - 1)
+    assert np.array_equal(np_, (n_ + PS - 1) // PS)
+    assert np.array_equal(strip0, np.concatenate([[0], np.cumsum(np_)[:-1]])) and nstrips == np_.sum()
+    col2node = np.repeat(np.arange(nn), n_)
+    idx = [rlist[rptr[k] - 1:rptr[k + 1] - 1] - 1 for k in range(nn)]
+    for k in range(nn):
+        p = sparent[k] - 1
+        assert pflag[k] == (strip0[p] if p < nn else -1)
+
+    # ---- forward
+    flags = np.zeros(nstrips, bool)
+    cnt = np.zeros(nn, np.int64)
+    rows_done = [np.zeros(m_[k], np.int32) for k in range(nn)]
+
+    def fwd_below(k, r0, r1, db, dc):
+        assert flags[strip0[k]:strip0[k] + np_[k]].all()          # waits only on earlier tasks
+        want = col2node[idx[k][r0:r1]]
+        want = want[np.concatenate([[True], np.diff(want) != 0])] if len(want) else want
+        assert np.array_equal(dest[db:db + dc], want)
+        for d in want:
+            assert not flags[strip0[d]]                            # lands before the ancestor reads
+            cnt[d] += 1
+        rows_done[k][r0:r1] += 1
+
+    for node, kind, r0, nrows, db, dc in tf:
+        if kind in (DIAG, SMALLK):
+            i = r0 if kind == DIAG else 0
+            assert flags[strip0[node]:strip0[node] + i].all() and not flags[strip0[node] + i]
+            if i == 0:
+                assert cnt[node] == exp_f[node]
+            flags[strip0[node] + i] = True
+            rows_done[node][i * PS:min((i + 1) * PS, n_[node])] += 1
+            if kind == SMALLK:
+                assert np_[node] == 1
+                fwd_below(node, n_[node], m_[node], db, dc)
+        else:
+            assert r0 >= n_[node] and 0 < nrows <= PS
+            fwd_below(node, r0, r0 + nrows, db, dc)
+    assert flags.all() and np.array_equal(cnt, exp_f)
+    assert all((r == 1).all() for r in rows_done)
+
+    # ---- backward
+    flags[:] = False
+    cntb = np.zeros(nn, np.int64)
+    rows_done = [np.zeros(m_[k], np.int32) for k in range(nn)]
+
+    def bwd_below(k, r0, r1):
+        assert pflag[k] < 0 or flags[pflag[k]]
+        for d in np.unique(col2node[idx[k][r0:r1]]):
+            assert flags[strip0[d]:strip0[d] + np_[d]].all()       # every ancestor touched is complete
+        assert not flags[strip0[k]:strip0[k] + np_[k]].any()
+        rows_done[k][r0:r1] += 1
+
+    for node, kind, r0, nrows, db, dc in tb:
+        if kind == BELOW:
+            bwd_below(node, r0, r0 + nrows)
+            cntb[node] += 1
+            continue
+        if kind == SMALLK:
+            bwd_below(node, n_[node], m_[node])
+            i = 0
+        else:
+            i = r0
+            if i == np_[node] - 1:
+                assert cntb[node] == exp_b[node]
+        f0 = strip0[node]
+        assert flags[f0 + i + 1:f0 + np_[node]].all() and not flags[f0 + i]
+        flags[f0 + i] = True
+        rows_done[node][i * PS:min((i + 1) * PS, n_[node])] += 1
+    assert flags.all() and np.array_equal(cntb, exp_b)
+    assert all((r == 1).all() for r in rows_done)
+
+
+NUMERIC = [c for c in CASES if c[0] in ("tri3", "n1", "p2d-20-nb16", "p3d-10-nb32", "p3d-9x7x5-nb33",
+                                        "rand300-dense", "el3d-6-nb128", "p3d-24-nb64", "rand300-dense-nb32")]
+
+
+@pytest.mark.parametrize("case", NUMERIC, ids=ids(NUMERIC))
+def test_lists_replayed_numerically(case):
+    """Execute the task lists with numpy on the oracle's factor: same decomposition as the CUDA
+    kernels (strip gathers, below-row scatters with counters, transposed gathers)."""
+    s, (n, ptr, row, val), (sptr, sparent, rptr, rlist) = tables(case)
+    name, mk, nb, ncpu, prune = case
+    tf, tb, nd, dest, nstrips = s.pipe_tables()
+    nn = s.nnodes
+    m_, n_, sa, strip0, np_, exp_f, exp_b, pflag = nd.T
+    o = Oracle(n, ptr, row, s.order, sptr, sparent, rptr, rlist, nb, ncpu=ncpu, prune=prune)
+    o.factor(val, 1)
+    fo = o.factor_entries()
+    # node matrices (m x n) from the reference layout (block columns, rows [c nb, m) x width)
+    Ls, pos = [], 0
+    for k in range(nn):
+        L = np.zeros((m_[k], n_[k]))
+        for c0 in range(0, n_[k], nb):
+            w = min(nb, n_[k] - c0)
+            h = m_[k] - c0
+            L[c0:, c0:c0 + w] = fo[pos:pos + h * w].reshape(h, w)
+            pos += h * w
+        L[:n_[k], :n_[k]] = np.tril(L[:n_[k], :n_[k]])
+        Ls.append(L)
+    idx = [rlist[rptr[k] - 1:rptr[k + 1] - 1] - 1 for k in range(nn)]
+    nrhs = 3
+    xs = np.asfortranarray(np.tile(np.arange(1.0, nrhs + 1), (n, 1)) + 0.25 * np.sin(np.arange(n))[:, None])
+    b = np.asfortranarray(M.matvec(n, ptr, row, val, xs))
+    porder = np.argsort(s.order[:n] - 1)          # pivot position -> variable
+    xw = b[porder, :].copy()
+
+    def strip(k, i):
+        return slice(i * PS, min((i + 1) * PS, n_[k]))
+
+    def fwd_below(k, r0, r1):
+        xw[idx[k][r0:r1]] -= Ls[k][r0:r1, :] @ xw[sa[k]:sa[k] + n_[k]]
+
+    for node, kind, r0, nrows, db, dc in tf:
+        if kind != BELOW:
+            sl = strip(node, r0 if kind == DIAG else 0)
+            L = Ls[node]
+            rhs = xw[sa[node] + sl.start:sa[node] + sl.stop] - L[sl, :sl.start] @ xw[sa[node]:sa[node] + sl.start]
+            xw[sa[node] + sl.start:sa[node] + sl.stop] = np.linalg.solve(L[sl, sl], rhs)
+            if kind == SMALLK:
+                fwd_below(node, n_[node], m_[node])
+        else:
+            fwd_below(node, r0, r0 + nrows)
+
+    def bwd_below(k, r0, r1):
+        xw[sa[k]:sa[k] + n_[k]] -= Ls[k][r0:r1, :].T @ xw[idx[k][r0:r1]]
+
+    for node, kind, r0, nrows, db, dc in tb:
+        if kind == BELOW:
+            bwd_below(node, r0, r0 + nrows)
+            continue
+        if kind == SMALLK:
+            bwd_below(node, n_[node], m_[node])
+        sl = strip(node, r0 if kind == DIAG else 0)
+        L = Ls[node]
+        lo, hi = sa[node] + sl.stop, sa[node] + n_[node]
+        rhs = xw[sa[node] + sl.start:sa[node] + sl.stop] - L[sl.stop:n_[node], sl].T @ xw[lo:hi]
+        xw[sa[node] + sl.start:sa[node] + sl.stop] = np.linalg.solve(L[sl, sl].T, rhs)
+    x = np.empty_like(xw)
+    x[porder, :] = xw
+    x = np.asfortranarray(x)
+    ok, err = chkerr(n, ptr, row, val, x, b)
+    assert ok == nrhs and err.max() <= 1e-14, err
