@@ -88,9 +88,15 @@ void spllt_b200_profile_solve(void *fkeep, int nrhs, double *d_x, int ldx, doubl
  * deadlock free).  sizes: out4 = {forward tasks, backward tasks, strips, dest entries};
  * tasks: 6 ints each {node (0-based), kind (0 diag strip, 1 below chunk, 2 fused small node), r0,
  * nrows, dest_begin, dest_count}; nodes: 8 ints each {m, n, sa, strip0, np, expect_f, expect_b,
- * pflag}; dest: node ids */
+ * pflag}; dest: global strip ids (forward: counters the task bumps, backward: flags it waits for);
+ * expect: per strip, how many forward tasks add into its rows */
 void spllt_b200_pipe_sizes(void *akeep, long long *out4);
-void spllt_b200_get_pipe(void *akeep, int *tasks_f, int *tasks_b, int *nodes, int *dest);
+/* diagnostic: one un-graphed solve with 8 globaltimer stamps (ns) per claimed task of the persistent
+ * kernels {start, waits satisfied, solved, end, 4 strip-internal}; out_f / out_b hold 8 * tasks * ceil(nrhs / rc) values
+ * (rc = 1 for nrhs == 1, else 4), in claim order */
+void spllt_b200_trace_solve(void *fkeep, int nrhs, double *d_x, int ldx, unsigned long long *out_f,
+                            unsigned long long *out_b);
+void spllt_b200_get_pipe(void *akeep, int *tasks_f, int *tasks_b, int *nodes, int *dest, int *expect);
 
 /* ---- FP64 peak probes (no FP64 figure in MEASURED_PEAKS.json): enqueue a register-resident
  * DMMA (kind 0) or DFMA (kind 1) loop on every SM; returns the flops it will execute */

@@ -108,8 +108,10 @@ def load_library(path=None):
         "spllt_b200_node_owner": (C.c_int, [vp, C.c_int]),
         "spllt_b200_profile_solve": (None, [vp, C.c_int, vp, C.c_int, dp, C.c_char_p]),
         "spllt_b200_pipe_sizes": (None, [vp, C.POINTER(C.c_longlong)]),
+        "spllt_b200_trace_solve": (None, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_ulonglong),
+                                          C.POINTER(C.c_ulonglong)]),
         "spllt_b200_get_pipe": (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                       C.POINTER(C.c_int)]),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "spllt_b200_peak_probe": (C.c_double, [C.c_int, C.c_int, vp]),
         "spllt_b200_arena_ptr": (vp, [vp]),
         "spllt_b200_partition": (None, [vp, vp, C.c_int, C.c_int]),
@@ -269,8 +271,20 @@ class SpLLT:
                                         csv.encode() if csv else None)
         return dict(zip(("fwd_diag", "fwd_upd", "bwd_upd", "bwd_diag", "fwd_pipe", "bwd_pipe"), ms.tolist()))
 
+    def trace_solve(self, d_x_ptr, nrhs):
+        """Per-task time stamps (ns) of the persistent solve kernels: (fwd [k,8], bwd [k,8])."""
+        sz = np.zeros(4, np.int64)
+        self.L.spllt_b200_pipe_sizes(self.akeep, sz.ctypes.data_as(C.POINTER(C.c_longlong)))
+        ch = 1 if nrhs == 1 else (nrhs + 3) // 4
+        f = np.zeros((int(sz[0]) * ch, 8), np.uint64)
+        b = np.zeros((int(sz[1]) * ch, 8), np.uint64)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_ulonglong))
+        self.L.spllt_b200_trace_solve(self.fkeep, nrhs, C.c_void_p(d_x_ptr), self.n, up(f), up(b))
+        return f, b
+
     def pipe_tables(self):
-        """Work lists of the pipelined solve: (tasks_f [k,6], tasks_b [k,6], nodes [nnodes,8], dest)."""
+        """Work lists of the pipelined solve:
+        (tasks_f [k,6], tasks_b [k,6], nodes [nnodes,8], dest, nstrips, expect [nstrips])."""
         sz = np.zeros(4, np.int64)
         self.L.spllt_b200_pipe_sizes(self.akeep, sz.ctypes.data_as(C.POINTER(C.c_longlong)))
         tf = np.zeros((int(sz[0]), 6), np.int32)
@@ -278,8 +292,9 @@ class SpLLT:
         nd = np.zeros((self.nnodes, 8), np.int32)
         de = np.zeros(max(int(sz[3]), 1), np.int32)
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
-        self.L.spllt_b200_get_pipe(self.akeep, ip(tf), ip(tb), ip(nd), ip(de))
-        return tf, tb, nd, de[:int(sz[3])], int(sz[2])
+        ex = np.zeros(max(int(sz[2]), 1), np.int32)
+        self.L.spllt_b200_get_pipe(self.akeep, ip(tf), ip(tb), ip(nd), ip(de), ip(ex))
+        return tf, tb, nd, de[:int(sz[3])], int(sz[2]), ex[:int(sz[2])]
 
     def pivot_flag(self):
         return self.L.spllt_b200_pivot_flag(self.fkeep)

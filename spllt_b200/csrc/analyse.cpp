@@ -728,6 +728,9 @@ static void build_pipe_schedule(Analysis& A) {
     strip += p.np;
   }
   A.nstrips = strip;
+  A.strip_node.assign(strip, 0);
+  for (int s = 0; s < nn; ++s)
+    for (int i = 0; i < A.pnodes[s].np; ++i) A.strip_node[A.pnodes[s].strip0 + i] = s;
   for (int s = 0; s < nn; ++s)
     if (A.nodes[s].parent >= 0) A.pnodes[s].pflag = A.pnodes[A.nodes[s].parent].strip0;
   std::vector<int> ord;
@@ -735,20 +738,35 @@ static void build_pipe_schedule(Analysis& A) {
     if (A.nodes[s].depth0 >= cut) ord.push_back(s);
   std::stable_sort(ord.begin(), ord.end(),
                    [&](int a, int b) { return A.nodes[a].depth0 < A.nodes[b].depth0; });
+  A.pexpect.assign(strip, 0);
   auto dests = [&](int s, int r0, int r1, int* begin, int* count) {
-    // distinct ancestor nodes owning rows [r0, r1) of node s (index is sorted => runs)
+    // distinct ancestor STRIPS owning rows [r0, r1) of node s (index is sorted => runs).
+    // forward: the strips whose counters the task bumps; backward: the strips it waits for.
     *begin = (int)A.pipe_dest.size();
     const int* idx = A.index.data() + A.nodes[s].idx_off;
     int last = -1;
     for (int r = r0; r < r1; ++r) {
-      int d = A.col2node[idx[r]];
-      if (d != last) {
-        A.pipe_dest.push_back(d);
+      const int d = A.col2node[idx[r]];
+      const int st = A.pnodes[d].strip0 + (idx[r] - A.nodes[d].sa) / PS;
+      if (st != last) {
+        A.pipe_dest.push_back(st);
+        A.pexpect[st]++;
         A.pnodes[d].expect_f++;
-        last = d;
+        last = st;
       }
     }
     *count = (int)A.pipe_dest.size() - *begin;
+  };
+  // rows per BELOW task of a narrow node: large chunks where a tree level has many nodes, small
+  // ones near the top where a few tall nodes must be spread over the whole device
+  std::vector<i64> below_rows(A.ndepth + 1, 0);
+  auto is_small0 = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
+  for (int s : ord)
+    if (!is_small0(A.nodes[s]) && A.pnodes[s].np <= PIPE_FAT_NP) below_rows[A.nodes[s].depth0] += A.nodes[s].m - A.nodes[s].n;
+  auto chunk_of = [&](int s) {
+    if (A.pnodes[s].np > PIPE_FAT_NP) return PS;
+    i64 c = (below_rows[A.nodes[s].depth0] / PIPE_LEVEL_TASKS + PS - 1) / PS * PS;
+    return (int)std::max<i64>(PS, std::min<i64>(PIPE_FAT_ROWS, c));
   };
   auto is_small = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
   for (int s : ord) {
@@ -760,21 +778,27 @@ static void build_pipe_schedule(Analysis& A) {
       continue;
     }
     for (int i = 0; i < A.pnodes[s].np; ++i) A.ptasks_f.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
-    for (int r = nd.n; r < nd.m; r += PS) {
-      PTask t{s, P_BELOW, r, std::min(PS, nd.m - r), 0, 0, {0, 0}};
+    const int chunk = chunk_of(s);
+    for (int r = nd.n; r < nd.m; r += chunk) {
+      PTask t{s, P_BELOW, r, std::min(chunk, nd.m - r), 0, 0, {0, 0}};
       dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
       A.ptasks_f.push_back(t);
     }
   }
+  // the backward tasks reuse the forward tasks' strip lists (same row ranges)
+  std::vector<std::vector<PTask>> of_node(nn);
+  for (const PTask& t : A.ptasks_f)
+    if (t.kind != P_DIAG) of_node[t.node].push_back(t);
   for (auto it = ord.rbegin(); it != ord.rend(); ++it) {
     const int s = *it;
     const HNode& nd = A.nodes[s];
     if (is_small(nd)) {
-      A.ptasks_b.push_back(PTask{s, P_SMALL, 0, 0, 0, 0, {0, 0}});
+      A.ptasks_b.push_back(of_node[s][0]);
       continue;
     }
-    for (int r = nd.n; r < nd.m; r += PS) {
-      A.ptasks_b.push_back(PTask{s, P_BELOW, r, std::min(PS, nd.m - r), 0, 0, {0, 0}});
+    // bottom chunk first: its rows belong to the highest ancestors, which finish first
+    for (auto t = of_node[s].rbegin(); t != of_node[s].rend(); ++t) {
+      A.ptasks_b.push_back(*t);
       A.pnodes[s].expect_b++;
     }
     for (int i = A.pnodes[s].np - 1; i >= 0; --i) A.ptasks_b.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});

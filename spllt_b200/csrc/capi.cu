@@ -517,6 +517,10 @@ void spllt_b200_profile_solve(void* fkeep, int nrhs, double* d_x, int ldx, doubl
   EE(fkeep)->profile_solve(d_x, ldx, nrhs, ms6, csv);
 }
 
+void spllt_b200_trace_solve(void* fkeep, int nrhs, double* d_x, int ldx, unsigned long long* out_f,
+                            unsigned long long* out_b) {
+  EE(fkeep)->trace_solve(d_x, ldx, nrhs, out_f, out_b);
+}
 void spllt_b200_pipe_sizes(void* akeep, long long* out4) {
   const Analysis& A = *AA(akeep);
   out4[0] = (long long)A.ptasks_f.size();
@@ -524,7 +528,7 @@ void spllt_b200_pipe_sizes(void* akeep, long long* out4) {
   out4[2] = A.nstrips;
   out4[3] = (long long)A.pipe_dest.size();
 }
-void spllt_b200_get_pipe(void* akeep, int* tasks_f, int* tasks_b, int* nodes, int* dest) {
+void spllt_b200_get_pipe(void* akeep, int* tasks_f, int* tasks_b, int* nodes, int* dest, int* expect) {
   const Analysis& A = *AA(akeep);
   auto put = [](const std::vector<PTask>& v, int* o) {
     for (const PTask& t : v) {
@@ -538,6 +542,7 @@ void spllt_b200_get_pipe(void* akeep, int* tasks_f, int* tasks_b, int* nodes, in
     *nodes++ = p.np; *nodes++ = p.expect_f; *nodes++ = p.expect_b; *nodes++ = p.pflag;
   }
   for (int d : A.pipe_dest) *dest++ = d;
+  for (int e : A.pexpect) *expect++ = e;
 }
 double spllt_b200_peak_probe(int kind, int iters, void* stream) {
   require_gpu();
@@ -593,6 +598,7 @@ void spllt_b200_get_launch_records(void* akeep, long long* out) {
 void spllt_b200_run_launches(void* fkeep, long long first, long long last) {
   Engine* e = EE(fkeep);
   e->upload_tables();
+  e->dinv_valid = false;
   for (long long i = first; i < last; ++i) e->launch_one(e->A->launches[i], e->stream, false);
 }
 // block column c (0-based) of node (1-based): arena offset, leading dimension, rows, columns
@@ -615,6 +621,7 @@ void spllt_b200_unpack_bcol(void* akeep, void* fkeep, int node, int c, const dou
   long long off; int ld, rows, cols;
   spllt_b200_bcol_region(akeep, node, c, &off, &ld, &rows, &cols);
   Engine* e = EE(fkeep);
+  e->dinv_valid = false;
   launch_unpack(e->arena + off, ld, rows, cols, d_buf, e->stream);
 }
 int spllt_b200_dist_top(void* akeep) { return AA(akeep)->dist_top; }
@@ -623,6 +630,7 @@ void spllt_b200_factor_phase(void* akeep, void* fkeep, const double* d_val, int 
   (void)akeep;
   Engine* e = EE(fkeep);
   e->upload_tables();
+  e->dinv_valid = false;   // the caller completes the factor; inverses are recomputed before the next solve
   e->enqueue_factor(d_val, e->stream, phase);
 }
 

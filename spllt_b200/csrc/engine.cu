@@ -134,6 +134,9 @@ void Engine::upload_tables() {
   d_ptask_f = upload(S.ptasks_f);
   d_ptask_b = upload(S.ptasks_b);
   d_pdest = upload(S.pipe_dest);
+  d_strip_node = upload(S.strip_node);
+  d_pexpect = upload(S.pexpect);
+  CK(cudaMalloc(&d_dinv, std::max<i64>((i64)S.nstrips * PS * PS, 1) * sizeof(double)));
   d_index = upload(S.index);
   d_porder = upload(S.porder);
   int maxw = 1;
@@ -252,6 +255,8 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     launch_one(L, st, false);
   }
   join_bg(1 << 30);
+  // last launch of a complete factorization: inverses of the diagonal blocks for the solve phase
+  if (phase < 0) launch_invert_diag(d_pnodes, d_strip_node, S.nstrips, arena, d_dinv, st);
 }
 
 void Engine::factor(const double* dval) {
@@ -277,12 +282,14 @@ void Engine::factor(const double* dval) {
   else
     enqueue_factor(dval, stream, -1);
   factored = true;
+  dinv_valid = true;   // enqueue_factor(phase -1) ends with launch_invert_diag
 }
 
 // Un-graphed factorization with one event pair per launch: milliseconds per kernel kind
 // (assemble+memset, panel, tile_s, tile_l) and, optionally, one CSV line per launch.
 void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   upload_tables();
+  dinv_valid = false;
   for (int i = 0; i < 4; ++i) ms4[i] = 0;
   if (A->n == 0) return;
   const Analysis& S = *A;
@@ -362,11 +369,11 @@ void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
       launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
       launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
     }
-    launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs,
+    launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
                       S.nstrips, S.nnodes, d_psync, st);
   }
   if (job == 0 || job == 2) {
-    launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs,
+    launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
                       S.nstrips, S.nnodes, d_psync + psync_ints, st);
     for (int d = S.ndepth - 1; d >= 0; --d) {
       const SolveLaunch& L = S.slaunch[d];
@@ -376,10 +383,20 @@ void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
   }
 }
 
+// The pipelined solve multiplies by the inverses of the 64 x 64 diagonal blocks.  A single-GPU
+// factorization computes them as its last launch; after any other way of producing the factor
+// (multi-GPU phases, diagnostics) they are computed before the first solve.
+void Engine::ensure_dinv() {
+  if (dinv_valid) return;
+  launch_invert_diag(d_pnodes, d_strip_node, A->nstrips, arena, d_dinv, stream);
+  dinv_valid = true;
+}
+
 void Engine::solve(double* dx, int ldx, int nrhs, int job) {
   upload_tables();
   if (A->n == 0 || nrhs <= 0) return;
   ensure_solve_buffers(nrhs);
+  ensure_dinv();
   if (job == 0 || job == 1) launch_permute_in(dx, ldx, d_porder, d_xw, A->n, nrhs, stream);
   if (use_graph) {
     SolveGraphKey key{nullptr, 0, nrhs, job, stream, d_xw};
@@ -413,6 +430,7 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
   for (int i = 0; i < 6; ++i) ms6[i] = 0;
   if (A->n == 0) return;
   ensure_solve_buffers(nrhs);
+  ensure_dinv();
   const Analysis& S = *A;
   cudaStream_t st = stream;
   struct Rec {
@@ -439,11 +457,11 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
     mark();
     recs.push_back({1, d, L.upd_count});
   }
-  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs, S.nstrips,
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
                     S.nnodes, d_psync, st);
   mark();
   recs.push_back({4, -1, (long long)S.ptasks_f.size()});
-  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, arena, d_index, d_xw, nrhs,
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
                     S.nstrips, S.nnodes, d_psync + psync_ints, st);
   mark();
   recs.push_back({5, -1, (long long)S.ptasks_b.size()});
@@ -469,6 +487,44 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
   }
   if (f) fclose(f);
   for (auto& x : ev) CK(cudaEventDestroy(x));
+}
+
+// One un-graphed forward + backward solve with per-task time stamps (globaltimer, ns) from the
+// persistent kernels: out_f / out_b get 8 stamps per claimed task (claim order x rhs chunk):
+// start, waits satisfied, solved, end, + 4 strip-internal stamps.  Diagnostic only.
+void Engine::trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_f, unsigned long long* out_b) {
+  upload_tables();
+  if (A->n == 0) return;
+  ensure_solve_buffers(nrhs);
+  ensure_dinv();
+  const Analysis& S = *A;
+  const size_t nf = S.ptasks_f.size() * (size_t)pipe_chunks(nrhs) * 8, nbk = S.ptasks_b.size() * (size_t)pipe_chunks(nrhs) * 8;
+  unsigned long long *tf = nullptr, *tb = nullptr;
+  CK(cudaMalloc(&tf, std::max<size_t>(nf, 1) * 8));
+  CK(cudaMalloc(&tb, std::max<size_t>(nbk, 1) * 8));
+  CK(cudaMemset(tf, 0, std::max<size_t>(nf, 1) * 8));
+  CK(cudaMemset(tb, 0, std::max<size_t>(nbk, 1) * 8));
+  launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, stream);
+  for (int d = 0; d < S.ndepth; ++d) {
+    const SolveLaunch& L = S.slaunch[d];
+    launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, stream);
+    launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
+  }
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
+                    S.nnodes, d_psync, stream, tf);
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+                    S.nstrips, S.nnodes, d_psync + psync_ints, stream, tb);
+  for (int d = S.ndepth - 1; d >= 0; --d) {
+    const SolveLaunch& L = S.slaunch[d];
+    launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
+    launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, stream);
+  }
+  launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, stream);
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaMemcpy(out_f, tf, nf * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out_b, tb, nbk * 8, cudaMemcpyDeviceToHost));
+  CK(cudaFree(tf));
+  CK(cudaFree(tb));
 }
 
 void Engine::solve_host(double* x, int nrhs, int job) {
@@ -538,6 +594,9 @@ void Engine::release() {
   cudaFree(d_ptask_f);
   cudaFree(d_ptask_b);
   cudaFree(d_pdest);
+  cudaFree(d_strip_node);
+  cudaFree(d_pexpect);
+  cudaFree(d_dinv);
   if (d_psync) cudaFree(d_psync);
   d_psync = nullptr;
   cudaFree(d_index);

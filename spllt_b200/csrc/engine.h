@@ -57,6 +57,10 @@ struct Engine {
   PTask* d_ptask_f = nullptr;
   PTask* d_ptask_b = nullptr;
   int* d_pdest = nullptr;
+  int* d_strip_node = nullptr;
+  int* d_pexpect = nullptr;
+  double* d_dinv = nullptr;       // [nstrips][64][64] inverses of the diagonal blocks
+  bool dinv_valid = false;
   int* d_psync = nullptr;         // flags + counters: forward region, then backward region
   i64 psync_ints = 0;             // ints per region
   int* d_index = nullptr;
@@ -82,8 +86,10 @@ struct Engine {
   void profile_factor(const double* dval, double* ms5, const char* csv);
   void launch_one(const Launch& L, cudaStream_t st, bool background);
   void enqueue_solve(int nrhs, int job, cudaStream_t st);
+  void ensure_dinv();
   void solve(double* dx, int ldx, int nrhs, int job);
   void profile_solve(double* dx, int ldx, int nrhs, double* ms6, const char* csv);
+  void trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_f, unsigned long long* out_b);
   void solve_host(double* x, int nrhs, int job);
   void sync();
   int pivot_flag();

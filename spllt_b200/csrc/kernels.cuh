@@ -44,14 +44,17 @@ void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double
 
 // pipelined solve (solve_pipe.cu): one persistent kernel per sweep
 constexpr int PIPE_RC = 4;   // right-hand sides per pass when nrhs > 1
-inline i64 pipe_sync_stride(int nstrips, int nnodes) { return ((i64)nstrips + nnodes + 31) / 32 * 32; }
+inline i64 pipe_sync_stride(int nstrips, int nnodes) { return (2 * (i64)nstrips + nnodes + 31) / 32 * 32; }
 void pipe_init();            // opt-in shared memory + resident grid sizes; call once per process
 int pipe_chunks(int nrhs);
 i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs);   // ints of flag / counter storage for one sweep
 // sync is zeroed (stream-ordered) before the kernel starts
-void launch_solve_pipe(bool fwd, const PTask* tasks, int ntasks, const PNode* nodes, const int* dest,
-                       const double* arena, const int* index, double* xw, int nrhs, int nstrips, int nnodes,
-                       int* sync, cudaStream_t st);
+void launch_solve_pipe(bool fwd, const PTask* tasks, int ntasks, const PNode* nodes, const int* dest, const int* expect,
+                       const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
+                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace = nullptr);
+// inverses of the 64 x 64 diagonal blocks of every strip, dinv[strip][64][64] (once per factorization)
+void launch_invert_diag(const PNode* nodes, const int* strip_node, int nstrips, const double* arena, double* dinv,
+                        cudaStream_t st);
 
 // FP64 tensor-pipe peak probe: every warp of every SM runs register-resident DMMA.
 // Returns flops issued; time it with events.

@@ -121,6 +121,9 @@ struct SolveLaunch {
 // below it (a14/a15), independent of the factorization's nb.
 constexpr int PS = 64;           // strip width of the pipelined solve
 constexpr int PIPE_SMALL_ROWS = 256;  // nodes with n <= PS and m - n <= this are one fused task
+constexpr int PIPE_FAT_NP = 4;        // nodes with at most this many strips: rows below them are streamed in
+constexpr int PIPE_FAT_ROWS = 512;    //   chunks of up to this many rows after the whole node is solved
+constexpr int PIPE_LEVEL_TASKS = 512; // ... sized so that a tree level yields about this many chunks
 enum PipeKind { P_DIAG = 0, P_BELOW = 1, P_SMALL = 2 };
 struct PNode {
   i64 off;           // arena offset of the node
@@ -128,15 +131,16 @@ struct PNode {
   int ld, m, n, sa;
   int strip0;        // flag index of the node's first strip
   int np;            // strips = ceil(n / PS)
-  int expect_f;      // forward: tasks of descendants that add into this node's rows
+  int expect_f;      // forward: (task, strip) contributions into this node (informational; waits are per strip)
   int expect_b;      // backward: below-chunk tasks of this node
-  int pflag;         // backward: flag index of the parent's strip 0 (-1: root)
+  int pflag;         // flag index of the parent's strip 0 (-1: root); informational
   int pad[3];
 };
 struct PTask {
   int node, kind;
   int r0, nrows;     // P_DIAG: r0 = strip index; P_BELOW: rows [r0, r0 + nrows) of the node (r0 >= n)
-  int dest_begin, dest_count;  // forward: nodes whose counters this task bumps (pipe_dest)
+  int dest_begin, dest_count;  // ancestor strips its rows map to (pipe_dest): forward = counters it bumps,
+                               // backward = flags it waits for
   int pad[2];
 };
 
@@ -200,6 +204,8 @@ struct Analysis {
   std::vector<PNode> pnodes;          // [nnodes]
   std::vector<PTask> ptasks_f, ptasks_b;
   std::vector<int> pipe_dest;
+  std::vector<int> strip_node;        // [nstrips] owning node
+  std::vector<int> pexpect;           // [nstrips] forward: tasks that add into the strip's rows
 };
 
 // analyse.cpp

@@ -51,6 +51,9 @@ constexpr int PT = 256;            // threads per CTA
 constexpr int PWARPS = PT / 32;    // 8
 constexpr int RPW = PS / PWARPS;   // 8 rows of a strip per warp
 constexpr int PSL = PS + 1;        // padded leading dimension of the diagonal block in shared memory
+constexpr int FAT_NP = PIPE_FAT_NP;
+constexpr int PREFETCH_BYTES = 128 * 1024;   // per task
+static_assert(PS * PIPE_RC <= PT, "one right-hand-side entry of a strip per thread");
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -75,184 +78,310 @@ __device__ __forceinline__ void cp_commit_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// experiment switches (PipeArgs::mode, SPLLT_B200_PIPE_MODE):
+//   1: fence.acq_rel.gpu instead of __threadfence() (MEMBAR.SC) before a flag / counter is raised
+//   2: waiters back off (nanosleep) in proportion to their distance from the critical path
+//   4: poll with ld.relaxed (no L1 invalidation per poll); x is read with L2-coherent loads behind
+//      the control dependency   8: ... plus one fence.acq_rel after a successful poll
+//  16: no L2 prefetch of a task's rows at task start
+enum { M_FENCE_ACQREL = 1, M_BACKOFF = 2, M_POLL_RELAXED = 4, M_POLL_FENCE = 8, M_NO_PREFETCH = 16 };
+__device__ __forceinline__ void fence_gpu(int mode) {
+  if (mode & M_FENCE_ACQREL)
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  else
+    __threadfence();
+}
+
+// Rows [r0, r0 + nrows) x all n columns of a node -> L2, without registers: issued before a task
+// starts waiting, so that the streaming loops afterwards hit L2 (~0.3 us) instead of HBM (~1 us)
+// and more bytes are in flight than the register double-buffering alone allows.
+__device__ __forceinline__ void prefetch_l2(const double* base, i64 ld, int nrows, int ncols) {
+  const int row_bytes = ncols * 8;
+  const int rows = min(nrows, max(8, PREFETCH_BYTES / max(row_bytes, 1)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < rows; r += PWARPS) {
+    const char* p = (const char*)(base + (i64)r * ld);
+    for (int off = lane * 128; off < row_bytes; off += 32 * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+  }
+}
+
+// One instruction per warp: this warp's 8 rows x 64 columns (4 lines of 128 B per row) of a tile
+// -> L2.  The register loads of a tile are issued when its turn comes (while the warp polls for
+// the matching x_j); the HBM latency is taken two tiles earlier by this prefetch.
+__device__ __forceinline__ void prefetch_tile(const double* row0, i64 ld, int rows_valid, int cols_valid, int lane) {
+  const int u = lane >> 2, seg = lane & 3;
+  if (u < rows_valid && seg * 16 < cols_valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(row0 + (i64)u * ld + seg * 16));
+}
+
 // Flags f[0], f[dir], f[2 dir], ... (at most `limit` of them matter).  Spins until the first one
 // is raised and returns how many consecutive ones are (1..32): the caller skips polling for those.
-__device__ __forceinline__ int wait_run(const int* f, int dir, int limit, int lane) {
+// dist: how many publications this waiter is away from being on the critical path (>= 1).
+__device__ __forceinline__ int wait_run(const int* f, int dir, int limit, int lane, int mode, int dist) {
   for (;;) {
-    int v = lane < limit ? ld_acquire(f + dir * lane) : 0;
+    int v = 0;
+    if (lane < limit) v = (mode & M_POLL_RELAXED) ? ld_relaxed(f + dir * lane) : ld_acquire(f + dir * lane);
     unsigned b = __ballot_sync(FULL, v != 0);
     if (b & 1u) {
+      if (mode & M_POLL_FENCE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
       __syncwarp();
       return b == FULL ? 32 : __ffs(~b) - 1;
     }
+    if ((mode & M_BACKOFF) && dist > 1) __nanosleep(min(dist - 1, 16) * 200);
   }
 }
-__device__ __forceinline__ void wait_count(const int* c, int expect) {
-  while (ld_acquire(c) < expect) {
+__device__ __forceinline__ void wait_count(const int* c, int expect, int mode) {
+  if (mode & M_POLL_RELAXED) {
+    while (ld_relaxed(c) < expect) {
+    }
+    if (mode & M_POLL_FENCE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  } else {
+    while (ld_acquire(c) < expect) {
+    }
   }
 }
 
-struct Ctx {
+struct PipeArgs {
+  const PTask* tasks;
+  const PNode* nodes;
+  const int* dest;
+  const int* expect;   // [nstrips] forward: contributions a strip waits for
   const double* arena;
+  const double* dinv;
   const int* index;
   double* xw;
-  int nrhs, rc0, nr;
-  int* flags;
-  int* cnt;
-  double* Ls;   // [PS][PSL]
-  double* red;  // forward [PS][RC]; backward [PWARPS][PS][RC]
-  double* ys;   // backward below chunks: [PS][RC]
+  int* sync;        // [0] claim counter; per chunk c: flags at 32 + c*stride, node counters after the flags
+  int ntasks, nrhs, nchunk, stride, nstrips;
+  int mode;                    // experiment switches, see M_*
+  unsigned long long* trace;   // optional: 4 time stamps per claimed task
 };
 
-// diagonal block of strip i -> shared memory (lower triangle, rest zero), asynchronously
-__device__ __forceinline__ void fetch_diag(const PNode& nd, int r0, int rw, const Ctx& c) {
-  const double* D = c.arena + nd.off + (i64)r0 * nd.ld + r0;
-  for (int idx = threadIdx.x; idx < rw * PS; idx += PT) {
+extern __shared__ __align__(16) double pipe_sm[];
+// shared-memory layout (doubles): inverse diagonal block, backward partial sums, strip rhs, x of the node
+template <int RC>
+struct Sm {
+  static constexpr int LS = 0;                         // [PS][PSL]
+  static constexpr int RED = PS * PSL;                 // [PWARPS][PS][RC]
+  static constexpr int RH = RED + PWARPS * PS * RC;    // [PS][RC]   rhs of the strip / gathered y of a below pass
+  static constexpr int XS = RH + PS * RC;              // [FAT_NP * PS][RC]  x of the strip / of a narrow node
+  static constexpr int TOTAL = XS + FAT_NP * PS * RC;
+};
+
+struct Ctx {      // per task; everything else is read from the kernel parameters / shared memory
+  int rc0, nr;    // first right-hand side of this pass, how many (<= RC)
+  int* flags;
+  int* cnt;
+  unsigned long long* tr;   // optional time stamps (thread 0): start, waits done, solved, end
+};
+
+// inverse of the diagonal block of strip i -> shared memory (lower triangle, rest zero), asynchronously
+__device__ __forceinline__ void fetch_diag(const PNode& nd, int i, int rw, const PipeArgs& a, const Ctx& c) {
+  const double* D = a.dinv + (i64)(nd.strip0 + i) * (PS * PS);
+  for (int idx = threadIdx.x; idx < PS * PS; idx += PT) {
     const int r = idx >> 6, cc = idx & (PS - 1);
-    const bool ok = cc <= r;
-    cp_async8z(c.Ls + r * PSL + cc, ok ? D + (i64)r * nd.ld + cc : D, ok ? 8 : 0);
+    const bool ok = cc <= r && r < rw;
+    cp_async8z((pipe_sm + Sm<1>::LS) + r * PSL + cc, ok ? D + idx : D, ok ? 8 : 0);
   }
 }
 
 // x_i is final in global memory: make it visible, then raise the strip's flag
-template <int RC>
-__device__ __forceinline__ void publish(int* flag) {
-  if (RC == 1)
-    __syncwarp();   // only warp 0 wrote
-  else
-    __syncthreads();
+__device__ __forceinline__ void publish(int* flag, const PipeArgs& a, const Ctx& c) {
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (c.tr) c.tr[2] = gtime();
+    fence_gpu(a.mode);
     st_flag(flag, 1);
+    if (c.tr) c.tr[7] = gtime();
+  }
+}
+
+// x = Linv * rh (TRANS: Linv^T * rh) for one strip: thread r < 64 owns row r, four independent
+// accumulation chains; Ls is zero above the diagonal and rh is zero beyond the strip's width.
+template <int RC, bool TRANS>
+__device__ __forceinline__ void strip_matvec(int rw, double* xg, const PipeArgs& a, const Ctx& c) {
+  const int r = threadIdx.x;
+  if (r < PS) {
+    double s[4][RC];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < RC; ++q) s[p][q] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < PS; k += 4) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const double l = TRANS ? (pipe_sm + Sm<1>::LS)[(k + p) * PSL + r] : (pipe_sm + Sm<1>::LS)[r * PSL + k + p];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) s[p][q] = fma(l, (pipe_sm + Sm<RC>::RH)[(k + p) * RC + q], s[p][q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RC; ++q) {
+      const double x = (s[0][q] + s[1][q]) + (s[2][q] + s[3][q]);
+      (pipe_sm + Sm<RC>::XS)[r * RC + q] = x;
+      if (r < rw && q < c.nr) __stcg(xg + (i64)r * a.nrhs + q, x);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------ forward
 // DIAG(s, i), forward (a13 forward body + the intra-node part of a14).
 template <int RC>
-__device__ __forceinline__ void fwd_strip(const PNode& nd, int node, int i, const Ctx& c) {
+__device__ __forceinline__ void fwd_strip(const PNode& nd, int node, int i, bool pub, const PipeArgs& a, const Ctx& c) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = i * PS, rw = min(PS, nd.n - r0);
   const i64 ld = nd.ld;
-  fetch_diag(nd, r0, rw, c);
+  fetch_diag(nd, i, rw, a, c);
+  const int expect = a.expect[nd.strip0 + i];   // tasks of descendants that add into this strip's rows
+  // right-hand side of the strip: lane u < 8 of each warp owns row 8 warp + u.  It is final once
+  // every contribution has landed -- usually long before the x_j arrive, so fetch it now.
+  double* xg = a.xw + (i64)(nd.sa + r0) * a.nrhs + c.rc0;
+  const int row = warp * RPW + lane;
+  double b[RC];
+  int have_b = 1;
+  if (expect > 0) {
+    have_b = lane == 0 ? (ld_acquire(c.cnt + nd.strip0 + i) >= expect) : 0;
+    have_b = __shfl_sync(FULL, have_b, 0);
+  }
+  if (have_b) {
+#pragma unroll
+    for (int q = 0; q < RC; ++q)
+      b[q] = (lane < RPW && row < rw && q < c.nr) ? __ldcg(xg + (i64)row * a.nrhs + q) : 0.0;
+  }
   double acc[RPW][RC];
 #pragma unroll
   for (int u = 0; u < RPW; ++u)
 #pragma unroll
     for (int q = 0; q < RC; ++q) acc[u][q] = 0.0;
   if (i > 0) {
-    const double* Lr = c.arena + nd.off + (i64)(r0 + warp * RPW) * ld + 2 * lane;
-    double2 t[RPW], tn[RPW];
-#pragma unroll
-    for (int u = 0; u < RPW; ++u)
-      t[u] = (warp * RPW + u < rw) ? ld_stream2(Lr + (i64)u * ld) : make_double2(0.0, 0.0);
+    const double* Lw = a.arena + nd.off + (i64)(r0 + warp * RPW) * ld;   // this warp's first row
+    const double* Lr = Lw + 2 * lane;
+    const int rv = rw - warp * RPW;                                      // its valid rows
+    prefetch_tile(Lw, ld, rv, PS, lane);
+    if (i > 1) prefetch_tile(Lw + PS, ld, rv, PS, lane);
+    double2 t[RPW];
     int ready = 0;
     for (int j = 0; j < i; ++j) {
-      if (j + 1 < i) {
+      if (j + 2 < i) prefetch_tile(Lw + (j + 2) * PS, ld, rv, PS, lane);
 #pragma unroll
-        for (int u = 0; u < RPW; ++u)
-          tn[u] = (warp * RPW + u < rw) ? ld_stream2(Lr + (i64)u * ld + (j + 1) * PS) : make_double2(0.0, 0.0);
+      for (int u = 0; u < RPW; ++u) t[u] = (u < rv) ? ld_stream2(Lr + (i64)u * ld + j * PS) : make_double2(0.0, 0.0);
+      if (j >= ready) {
+        if (!have_b) {   // about to wait anyway: have the contributions landed meanwhile?
+          have_b = lane == 0 ? (ld_acquire(c.cnt + nd.strip0 + i) >= expect) : 0;
+          have_b = __shfl_sync(FULL, have_b, 0);
+          if (have_b) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q)
+              b[q] = (lane < RPW && row < rw && q < c.nr) ? __ldcg(xg + (i64)row * a.nrhs + q) : 0.0;
+          }
+        }
+        ready = j + wait_run(c.flags + nd.strip0 + j, 1, i - j, lane, a.mode, i - j);
       }
-      if (j >= ready) ready = j + wait_run(c.flags + nd.strip0 + j, 1, i - j, lane);
-      const double* xp = c.xw + (i64)(nd.sa + j * PS + 2 * lane) * c.nrhs + c.rc0;
+      if (c.tr && tid == 0 && j == i - 1) c.tr[4] = gtime();
+      const double* xp = a.xw + (i64)(nd.sa + j * PS + 2 * lane) * a.nrhs + c.rc0;
       double x0[RC], x1[RC];
 #pragma unroll
       for (int q = 0; q < RC; ++q) {
         x0[q] = q < c.nr ? __ldcg(xp + q) : 0.0;
-        x1[q] = q < c.nr ? __ldcg(xp + c.nrhs + q) : 0.0;
+        x1[q] = q < c.nr ? __ldcg(xp + a.nrhs + q) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < RPW; ++u)
 #pragma unroll
         for (int q = 0; q < RC; ++q) acc[u][q] = fma(t[u].x, x0[q], fma(t[u].y, x1[q], acc[u][q]));
-#pragma unroll
-      for (int u = 0; u < RPW; ++u) t[u] = tn[u];
     }
-#pragma unroll
-    for (int u = 0; u < RPW; ++u)
-#pragma unroll
-      for (int q = 0; q < RC; ++q) {
-        double v = acc[u][q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        acc[u][q] = v;
-      }
-  } else if (tid == 0 && nd.expect_f > 0) {
-    wait_count(c.cnt + node, nd.expect_f);   // every contribution of the descendants has landed
   }
-  if (lane == 0) {
+  if (c.tr && tid == 0) c.tr[5] = gtime() + (long long)(acc[0][0] == 12345.678);   // after the last FMA
+  if (!have_b) {   // every contribution to these 64 rows has landed (each warp reads its own rows)
+    if (lane == 0) wait_count(c.cnt + nd.strip0 + i, expect, a.mode);
+    __syncwarp();
 #pragma unroll
-    for (int u = 0; u < RPW; ++u)
-#pragma unroll
-      for (int q = 0; q < RC; ++q) c.red[(warp * RPW + u) * RC + q] = acc[u][q];
+    for (int q = 0; q < RC; ++q)
+      b[q] = (lane < RPW && row < rw && q < c.nr) ? __ldcg(xg + (i64)row * a.nrhs + q) : 0.0;
   }
+  {
+    if (i > 0) {
+#pragma unroll
+      for (int u = 0; u < RPW; ++u)
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          double v = acc[u][q];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+          if (lane == u) b[q] -= v;
+        }
+    }
+    if (lane < RPW) {
+#pragma unroll
+      for (int q = 0; q < RC; ++q) (pipe_sm + Sm<RC>::RH)[row * RC + q] = b[q];
+    }
+  }
+  if (c.tr && tid == 0) c.tr[1] = gtime();
   cp_commit_wait_all();
   __syncthreads();
-  double* xg = c.xw + (i64)(nd.sa + r0) * c.nrhs + c.rc0;
-  const double* Ls = c.Ls;
-  for (int q = warp; q < c.nr; q += PWARPS) {
-    const int i0 = lane, i1 = lane + 32;
-    double x0 = i0 < rw ? __ldcg(xg + (i64)i0 * c.nrhs + q) - c.red[i0 * RC + q] : 0.0;
-    double x1 = i1 < rw ? __ldcg(xg + (i64)i1 * c.nrhs + q) - c.red[i1 * RC + q] : 0.0;
-    const double d0 = i0 < rw ? 1.0 / Ls[i0 * PSL + i0] : 0.0, d1 = i1 < rw ? 1.0 / Ls[i1 * PSL + i1] : 0.0;
-    for (int k = 0; k < min(rw, 32); ++k) {
-      const double xk = __shfl_sync(FULL, x0 * d0, k);
-      if (lane == k) x0 = xk;
-      if (i0 > k) x0 -= Ls[i0 * PSL + k] * xk;
-      if (i1 < rw) x1 -= Ls[i1 * PSL + k] * xk;
-    }
-    for (int k = 32; k < rw; ++k) {
-      const double xk = __shfl_sync(FULL, x1 * d1, k - 32);
-      if (lane == k - 32) x1 = xk;
-      if (i1 > k && i1 < rw) x1 -= Ls[i1 * PSL + k] * xk;
-    }
-    if (i0 < rw) __stcg(xg + (i64)i0 * c.nrhs + q, x0);
-    if (i1 < rw) __stcg(xg + (i64)i1 * c.nrhs + q, x1);
-  }
-  publish<RC>(c.flags + nd.strip0 + i);
+  if (c.tr && tid == 0) c.tr[6] = gtime();
+  strip_matvec<RC, false>(rw, xg, a, c);
+  if (pub)
+    publish(c.flags + nd.strip0 + i, a, c);
+  else
+    __syncthreads();
 }
 
-// BELOW(s, rows [r0, r0+nrows)), forward (a14 slv_fwd_update + a15 fwd_update_upd):
-// xw[index[r]] -= L[r, 0..n) x_s, streaming over the node's strips as they are published.
+// BELOW(s, rows [r0, r0+nrows)), forward, nodes with many strips (a14 slv_fwd_update + a15
+// fwd_update_upd): xw[index[r]] -= L[r, 0..n) x_s, streaming over the node's strips as they are
+// published; nrows <= 64.
 template <int RC>
-__device__ __forceinline__ void fwd_below(const PNode& nd, int r0, int nrows, const Ctx& c) {
+__device__ __forceinline__ void fwd_below(const PNode& nd, int r0, int nrows, const PipeArgs& a, const Ctx& c) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const i64 ld = nd.ld;
   const int np = nd.np;
-  const double* Lr = c.arena + nd.off + (i64)(r0 + warp * RPW) * ld + 2 * lane;
+  const double* Lr = a.arena + nd.off + (i64)(r0 + warp * RPW) * ld + 2 * lane;
+  int myidx = 0;
+  if (lane < RPW && warp * RPW + lane < nrows) myidx = a.index[nd.idx_off + r0 + warp * RPW + lane];
   double acc[RPW][RC];
 #pragma unroll
   for (int u = 0; u < RPW; ++u)
 #pragma unroll
     for (int q = 0; q < RC; ++q) acc[u][q] = 0.0;
-  double2 t[RPW], tn[RPW];
-#pragma unroll
-  for (int u = 0; u < RPW; ++u)
-    t[u] = (warp * RPW + u < nrows && 2 * lane < nd.ld) ? ld_stream2(Lr + (i64)u * ld) : make_double2(0.0, 0.0);
+  const double* Lw = Lr - 2 * lane;       // this warp's first row
+  const int rv = nrows - warp * RPW;      // its valid rows
+  prefetch_tile(Lw, ld, rv, nd.ld, lane);
+  if (np > 1) prefetch_tile(Lw + PS, ld, rv, nd.ld - PS, lane);
+  double2 t[RPW];
   int ready = 0;
   for (int j = 0; j < np; ++j) {
-    if (j + 1 < np) {
-      const bool colok = (j + 1) * PS + 2 * lane < nd.ld;
+    if (j + 2 < np) prefetch_tile(Lw + (j + 2) * PS, ld, rv, nd.ld - (j + 2) * PS, lane);
+    const bool colok = j * PS + 2 * lane < nd.ld;
 #pragma unroll
-      for (int u = 0; u < RPW; ++u)
-        tn[u] = (warp * RPW + u < nrows && colok) ? ld_stream2(Lr + (i64)u * ld + (j + 1) * PS) : make_double2(0.0, 0.0);
-    }
-    if (j >= ready) ready = j + wait_run(c.flags + nd.strip0 + j, 1, np - j, lane);
+    for (int u = 0; u < RPW; ++u)
+      t[u] = (u < rv && colok) ? ld_stream2(Lr + (i64)u * ld + j * PS) : make_double2(0.0, 0.0);
+    if (j >= ready) ready = j + wait_run(c.flags + nd.strip0 + j, 1, np - j, lane, a.mode, np - j);
     const int col = j * PS + 2 * lane;
-    const double* xp = c.xw + (i64)(nd.sa + col) * c.nrhs + c.rc0;
+    const double* xp = a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0;
     double x0[RC], x1[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) {
       x0[q] = (q < c.nr && col < nd.n) ? __ldcg(xp + q) : 0.0;
-      x1[q] = (q < c.nr && col + 1 < nd.n) ? __ldcg(xp + c.nrhs + q) : 0.0;
+      x1[q] = (q < c.nr && col + 1 < nd.n) ? __ldcg(xp + a.nrhs + q) : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < RPW; ++u)
 #pragma unroll
       for (int q = 0; q < RC; ++q) acc[u][q] = fma(t[u].x, x0[q], fma(t[u].y, x1[q], acc[u][q]));
-#pragma unroll
-    for (int u = 0; u < RPW; ++u) t[u] = tn[u];
   }
+  double mine[RC];
+#pragma unroll
+  for (int q = 0; q < RC; ++q) mine[q] = 0.0;
 #pragma unroll
   for (int u = 0; u < RPW; ++u)
 #pragma unroll
@@ -260,25 +389,100 @@ __device__ __forceinline__ void fwd_below(const PNode& nd, int r0, int nrows, co
       double v = acc[u][q];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      acc[u][q] = v;
+      if (lane == u) mine[q] = v;
     }
-  const int* idx = c.index + nd.idx_off + r0 + warp * RPW;
+  if (lane < RPW && warp * RPW + lane < nrows) {
+    double* dst = a.xw + (i64)myidx * a.nrhs + c.rc0;
 #pragma unroll
-  for (int u = 0; u < RPW; ++u) {
-    if (lane == u && warp * RPW + u < nrows) {
-      double* dst = c.xw + (i64)idx[u] * c.nrhs + c.rc0;
+    for (int q = 0; q < RC; ++q)
+      if (q < c.nr) atomicAdd(dst + q, -mine[q]);
+  }
+}
+
+// BELOW, forward, nodes with at most FAT_NP strips (most of L's bytes live in the rows below
+// such nodes): the whole x_s is taken into registers once (from shared memory for the fused
+// SMALL task, else from global memory after all of the node's flags are up), then up to
+// PIPE_FAT_ROWS rows are streamed in passes of 64 with the next tile's loads always in flight.
+template <int RC>
+__device__ __forceinline__ void fwd_below_fat(const PNode& nd, int r0, int nrows, bool local, const PipeArgs& a, const Ctx& c) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const i64 ld = nd.ld;
+  const int np = nd.np;
+  const double* Lr = a.arena + nd.off + (i64)(r0 + warp * RPW) * ld + 2 * lane;
+  auto load_tile = [&](double2(&d)[RPW], int p, int j) {
+    const bool colok = j * PS + 2 * lane < nd.ld;
+#pragma unroll
+    for (int u = 0; u < RPW; ++u)
+      d[u] = (p * PS + warp * RPW + u < nrows && colok) ? ld_stream2(Lr + (i64)(p * PS + u) * ld + j * PS)
+                                                        : make_double2(0.0, 0.0);
+  };
+  double2 t[RPW];
+  if (!local) {
+    // x_s (n <= FAT_NP * 64 values per right-hand side) -> shared memory, once
+    if (warp == 0) {
+      int ready = 0;
+      while (ready < np) ready += wait_run(c.flags + nd.strip0 + ready, 1, np - ready, lane, a.mode, 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < np * PS * RC; k += PT) {
+      const int col = k / RC, q = k - col * RC;
+      (pipe_sm + Sm<RC>::XS)[k] = (col < nd.n && q < c.nr) ? __ldcg(a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0 + q) : 0.0;
+    }
+    __syncthreads();
+  }
+  if (c.tr && threadIdx.x == 0) c.tr[1] = gtime();
+  const int npass = (nrows + PS - 1) / PS;
+  for (int p = 0; p < npass; ++p) {
+    const int row = p * PS + warp * RPW + lane;
+    int myidx = 0;
+    if (lane < RPW && row < nrows) myidx = a.index[nd.idx_off + r0 + row];
+    double acc[RPW][RC];
+#pragma unroll
+    for (int u = 0; u < RPW; ++u)
+#pragma unroll
+      for (int q = 0; q < RC; ++q) acc[u][q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < FAT_NP; ++j) {
+      if (j < np) {
+        load_tile(t, p, j);
+        if (p + 1 < npass)   // next pass of this warp's rows -> L2 (the first 128 KB came in at task start)
+          prefetch_tile(Lr - 2 * lane + (i64)((p + 1) * PS) * ld + j * PS, ld, nrows - (p + 1) * PS - warp * RPW,
+                        nd.ld - j * PS, lane);
+#pragma unroll
+        for (int u = 0; u < RPW; ++u)
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            const double x0 = (pipe_sm + Sm<RC>::XS)[(j * PS + 2 * lane) * RC + q], x1 = (pipe_sm + Sm<RC>::XS)[(j * PS + 2 * lane + 1) * RC + q];
+            acc[u][q] = fma(t[u].x, x0, fma(t[u].y, x1, acc[u][q]));
+          }
+      }
+    }
+    double mine[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) mine[q] = 0.0;
+#pragma unroll
+    for (int u = 0; u < RPW; ++u)
+#pragma unroll
+      for (int q = 0; q < RC; ++q) {
+        double v = acc[u][q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == u) mine[q] = v;
+      }
+    if (lane < RPW && row < nrows) {
+      double* dst = a.xw + (i64)myidx * a.nrhs + c.rc0;
 #pragma unroll
       for (int q = 0; q < RC; ++q)
-        if (q < c.nr) atomicAdd(dst + q, -acc[u][q]);
+        if (q < c.nr) atomicAdd(dst + q, -mine[q]);
     }
   }
 }
 
 // the contributions above are complete: bump the counter of every ancestor node they hit
-__device__ __forceinline__ void bump_dests(const int* dest, int count, int* cnt) {
+__device__ __forceinline__ void bump_dests(const int* dest, int count, int* cnt, int mode) {
   __syncthreads();
   for (int k = threadIdx.x; k < count; k += PT) {
-    __threadfence();
+    fence_gpu(mode);
     atomicAdd(cnt + dest[k], 1);
   }
 }
@@ -287,209 +491,262 @@ __device__ __forceinline__ void bump_dests(const int* dest, int count, int* cnt)
 // DIAG(s, i), backward: x_i = L_ii^-T (b_i - sum_{j>i} L[strip j, strip i]^T x_j)
 // (a13 backward body + the intra-node part of slv_bwd_update).
 template <int RC>
-__device__ __forceinline__ void bwd_strip(const PNode& nd, int node, int i, bool wait_below, const Ctx& c) {
+__device__ __forceinline__ void bwd_strip(const PNode& nd, int node, int i, bool wait_below, const PipeArgs& a, const Ctx& c) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = i * PS, cw = min(PS, nd.n - r0);
   const i64 ld = nd.ld;
   const int np = nd.np, nj = np - 1 - i;
-  fetch_diag(nd, r0, cw, c);
-  if (wait_below && i == np - 1 && tid == 0 && nd.expect_b > 0) wait_count(c.cnt + node, nd.expect_b);
+  fetch_diag(nd, i, cw, a, c);
+  if (wait_below && i == np - 1 && tid == 0 && nd.expect_b > 0) wait_count(c.cnt + node, nd.expect_b, a.mode);
   double a0[RC], a1[RC];
 #pragma unroll
   for (int q = 0; q < RC; ++q) a0[q] = a1[q] = 0.0;
+  // this thread's entry of the strip's right-hand side (PS * RC <= PT entries); final as soon as
+  // any flag of the node is up (the node's last strip waited for the below counter)
+  double* xg = a.xw + (i64)(nd.sa + r0) * a.nrhs + c.rc0;
+  const int brow = tid / RC, bq = tid - brow * RC;
+  const bool bvalid = tid < PS * RC && brow < cw && bq < c.nr;
+  double bpre = 0.0;
   if (nj > 0) {
     // tile rows: strip j of the node, this warp's 8 rows; columns: strip i (full, since i < np-1)
-    const double* Lc = c.arena + nd.off + (i64)(warp * RPW) * ld + r0 + 2 * lane;
-    double2 t[RPW], tn[RPW];
-    {
-      const int rb = (np - 1) * PS + warp * RPW;
-#pragma unroll
-      for (int u = 0; u < RPW; ++u)
-        t[u] = (rb + u < nd.n) ? ld_stream2(Lc + (i64)((np - 1) * PS + u) * ld) : make_double2(0.0, 0.0);
-    }
+    const double* Lw = a.arena + nd.off + (i64)(warp * RPW) * ld + r0;   // this warp's rows of strip 0, column r0
+    const double* Lc = Lw + 2 * lane;
+    prefetch_tile(Lw + (i64)((np - 1) * PS) * ld, ld, nd.n - (np - 1) * PS - warp * RPW, PS, lane);
+    if (nj > 1) prefetch_tile(Lw + (i64)((np - 2) * PS) * ld, ld, RPW, PS, lane);
+    double2 t[RPW];
     int ready = 0;
     for (int jj = 0; jj < nj; ++jj) {
       const int j = np - 1 - jj;
-      if (jj + 1 < nj) {   // strip j-1 is a full strip
-#pragma unroll
-        for (int u = 0; u < RPW; ++u) tn[u] = ld_stream2(Lc + (i64)((j - 1) * PS + u) * ld);
-      }
-      if (jj >= ready) ready = jj + wait_run(c.flags + nd.strip0 + j, -1, nj - jj, lane);
+      if (jj + 2 < nj) prefetch_tile(Lw + (i64)((j - 2) * PS) * ld, ld, RPW, PS, lane);
       const int rb = j * PS + warp * RPW;
-      const double* xp = c.xw + (i64)(nd.sa + rb) * c.nrhs + c.rc0;
+#pragma unroll
+      for (int u = 0; u < RPW; ++u)
+        t[u] = (rb + u < nd.n) ? ld_stream2(Lc + (i64)(j * PS + u) * ld) : make_double2(0.0, 0.0);
+      if (jj >= ready) ready = jj + wait_run(c.flags + nd.strip0 + j, -1, nj - jj, lane, a.mode, nj - jj);
+      if (jj == 0 && bvalid) bpre = __ldcg(xg + (i64)brow * a.nrhs + bq);
+      if (c.tr && tid == 0 && jj == nj - 1) c.tr[4] = gtime();
+      const double* xp = a.xw + (i64)(nd.sa + rb) * a.nrhs + c.rc0;
 #pragma unroll
       for (int u = 0; u < RPW; ++u) {
         const bool ok = rb + u < nd.n;
 #pragma unroll
         for (int q = 0; q < RC; ++q) {
-          const double xv = (ok && q < c.nr) ? __ldcg(xp + (i64)u * c.nrhs + q) : 0.0;
+          const double xv = (ok && q < c.nr) ? __ldcg(xp + (i64)u * a.nrhs + q) : 0.0;
           a0[q] = fma(t[u].x, xv, a0[q]);
           a1[q] = fma(t[u].y, xv, a1[q]);
         }
       }
-#pragma unroll
-      for (int u = 0; u < RPW; ++u) t[u] = tn[u];
     }
   }
+  if (c.tr && tid == 0) c.tr[5] = gtime() + (long long)(a0[0] == 12345.678);
 #pragma unroll
   for (int q = 0; q < RC; ++q) {
-    c.red[(warp * PS + 2 * lane) * RC + q] = a0[q];
-    c.red[(warp * PS + 2 * lane + 1) * RC + q] = a1[q];
+    (pipe_sm + Sm<RC>::RED)[(warp * PS + 2 * lane) * RC + q] = a0[q];
+    (pipe_sm + Sm<RC>::RED)[(warp * PS + 2 * lane + 1) * RC + q] = a1[q];
+  }
+  if (c.tr && tid == 0) c.tr[1] = gtime();
+  __syncthreads();   // partial sums complete; for i == np-1 also: thread 0 has seen the below counter
+  if (nj == 0 && bvalid) bpre = __ldcg(xg + (i64)brow * a.nrhs + bq);
+  if (tid < PS * RC) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < PWARPS; ++w) s += (pipe_sm + Sm<RC>::RED)[(w * PS + brow) * RC + bq];
+    (pipe_sm + Sm<RC>::RH)[tid] = bvalid ? bpre - s : 0.0;
   }
   cp_commit_wait_all();
   __syncthreads();
-  double* xg = c.xw + (i64)(nd.sa + r0) * c.nrhs + c.rc0;
-  const double* Ls = c.Ls;
-  for (int q = warp; q < c.nr; q += PWARPS) {
-    const int i0 = lane, i1 = lane + 32;
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-    for (int w = 0; w < PWARPS; ++w) {
-      s0 += c.red[(w * PS + i0) * RC + q];
-      s1 += c.red[(w * PS + i1) * RC + q];
-    }
-    double x0 = i0 < cw ? __ldcg(xg + (i64)i0 * c.nrhs + q) - s0 : 0.0;
-    double x1 = i1 < cw ? __ldcg(xg + (i64)i1 * c.nrhs + q) - s1 : 0.0;
-    const double d0 = i0 < cw ? 1.0 / Ls[i0 * PSL + i0] : 0.0, d1 = i1 < cw ? 1.0 / Ls[i1 * PSL + i1] : 0.0;
-    // x_k = x_k / L_kk, then x_i -= L[k][i] x_k for i < k
-    for (int k = cw - 1; k >= 32; --k) {
-      const double xk = __shfl_sync(FULL, x1 * d1, k - 32);
-      if (lane == k - 32) x1 = xk;
-      if (i1 < k) x1 -= Ls[k * PSL + i1] * xk;
-      x0 -= Ls[k * PSL + i0] * xk;
-    }
-    for (int k = min(cw, 32) - 1; k >= 0; --k) {
-      const double xk = __shfl_sync(FULL, x0 * d0, k);
-      if (lane == k) x0 = xk;
-      if (i0 < k) x0 -= Ls[k * PSL + i0] * xk;
-    }
-    if (i0 < cw) __stcg(xg + (i64)i0 * c.nrhs + q, x0);
-    if (i1 < cw) __stcg(xg + (i64)i1 * c.nrhs + q, x1);
-  }
-  publish<RC>(c.flags + nd.strip0 + i);
+  if (c.tr && tid == 0) c.tr[6] = gtime();
+  strip_matvec<RC, true>(cw, xg, a, c);
+  publish(c.flags + nd.strip0 + i, a, c);
 }
 
 // BELOW(s, rows [r0, r0+nrows)), backward (a14 slv_bwd_update + a15 bwd_update_upd):
 // x_s -= L[rows, 0..n)^T xw[index[rows]].  The ancestors are complete when this runs.
+// Passes of 64 rows; within a pass the work items are (strip k, row group g).  Nodes with at
+// most FAT_NP strips give every warp at most one item, whose sums stay in registers across all
+// passes (one RED per column and task); wider nodes flush after every pass.
 template <int RC>
-__device__ __forceinline__ void bwd_below(const PNode& nd, int r0, int nrows, const Ctx& c) {
+__device__ __forceinline__ void bwd_below(const PNode& nd, int r0, int nrows, const PipeArgs& a, const Ctx& c) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const i64 ld = nd.ld;
   const int np = nd.np;
-  const int* idx = c.index + nd.idx_off + r0;
-  __syncthreads();   // ys may still be read by the previous chunk
-  for (int k = tid; k < PS * RC; k += PT) {
-    const int r = k / RC, q = k - r * RC;
-    c.ys[k] = (r < nrows && q < c.nr) ? __ldcg(c.xw + (i64)idx[r] * c.nrhs + c.rc0 + q) : 0.0;
-  }
-  __syncthreads();
-  // work items (strip k, row group g): enough of them to occupy the 8 warps of thin nodes,
-  // as few as possible otherwise (one RED per column and item)
   int rpi = (PS * np / PWARPS) & ~7;
-  rpi = max(8, min(PS, rpi));
-  const int ng = (nrows + rpi - 1) / rpi, nitems = np * ng;
-  const double* Lr = c.arena + nd.off + (i64)r0 * ld + 2 * lane;
-  for (int it = warp; it < nitems; it += PWARPS) {
-    const int k = it / ng, g = it - k * ng;
-    const int ra = g * rpi, rb = min(nrows, ra + rpi);
-    const int col = k * PS + 2 * lane;
-    const bool colok = col < nd.ld;
-    double a0[RC], a1[RC];
+  rpi = np == 3 ? 32 : max(8, min(PS, rpi));
+  const int ng = (PS + rpi - 1) / rpi, nitems = np * ng;
+  const bool keep = nitems <= PWARPS;   // np <= FAT_NP
+  const double* Lr = a.arena + nd.off + (i64)r0 * ld + 2 * lane;
+  double a0[RC], a1[RC];
 #pragma unroll
-    for (int q = 0; q < RC; ++q) a0[q] = a1[q] = 0.0;
-    for (int rbase = ra; rbase < rb; rbase += RPW) {
-      double2 t[RPW];
+  for (int q = 0; q < RC; ++q) a0[q] = a1[q] = 0.0;
+  const int npass = (nrows + PS - 1) / PS;
+  for (int p = 0; p < npass; ++p) {
+    const int cnt = min(PS, nrows - p * PS);
+    const int* idx = a.index + nd.idx_off + r0 + p * PS;
+    __syncthreads();   // rh may still be read by the previous pass / task
+    for (int k = tid; k < PS * RC; k += PT) {
+      const int r = k / RC, q = k - r * RC;
+      (pipe_sm + Sm<RC>::RH)[k] = (r < cnt && q < c.nr) ? __ldcg(a.xw + (i64)idx[r] * a.nrhs + c.rc0 + q) : 0.0;
+    }
+    __syncthreads();
+    if (c.tr && tid == 0 && p == 0) c.tr[1] = gtime();
+    for (int it = warp; it < nitems; it += PWARPS) {
+      const int k = it / ng, g = it - k * ng;
+      const int ra = g * rpi, rb = min(cnt, ra + rpi);
+      const int col = k * PS + 2 * lane;
+      const bool colok = col < nd.ld;
+      for (int rbase = ra; rbase < rb; rbase += RPW) {
+        double2 t[RPW];
 #pragma unroll
-      for (int u = 0; u < RPW; ++u)
-        t[u] = (rbase + u < rb && colok) ? ld_stream2(Lr + (i64)(rbase + u) * ld + k * PS) : make_double2(0.0, 0.0);
+        for (int u = 0; u < RPW; ++u)
+          t[u] = (rbase + u < rb && colok) ? ld_stream2(Lr + (i64)(p * PS + rbase + u) * ld + k * PS)
+                                           : make_double2(0.0, 0.0);
 #pragma unroll
-      for (int u = 0; u < RPW; ++u) {
-        const int r = min(rbase + u, PS - 1);
+        for (int u = 0; u < RPW; ++u) {
+          const int r = min(rbase + u, PS - 1);
 #pragma unroll
-        for (int q = 0; q < RC; ++q) {
-          const double y = c.ys[r * RC + q];
-          a0[q] = fma(t[u].x, y, a0[q]);
-          a1[q] = fma(t[u].y, y, a1[q]);
+          for (int q = 0; q < RC; ++q) {
+            const double y = (pipe_sm + Sm<RC>::RH)[r * RC + q];
+            a0[q] = fma(t[u].x, y, a0[q]);
+            a1[q] = fma(t[u].y, y, a1[q]);
+          }
         }
       }
-    }
-    double* dst = c.xw + (i64)(nd.sa + col) * c.nrhs + c.rc0;
+      if (!keep || p == npass - 1) {
+        double* dst = a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0;
 #pragma unroll
-    for (int q = 0; q < RC; ++q) {
-      if (q < c.nr && col < nd.n) atomicAdd(dst + q, -a0[q]);
-      if (q < c.nr && col + 1 < nd.n) atomicAdd(dst + c.nrhs + q, -a1[q]);
+        for (int q = 0; q < RC; ++q) {
+          if (q < c.nr && col < nd.n) atomicAdd(dst + q, -a0[q]);
+          if (q < c.nr && col + 1 < nd.n) atomicAdd(dst + a.nrhs + q, -a1[q]);
+          a0[q] = a1[q] = 0.0;
+        }
+      }
     }
   }
 }
 
 }  // namespace
 
-struct PipeArgs {
-  const PTask* tasks;
-  const PNode* nodes;
-  const int* dest;
-  const double* arena;
-  const int* index;
-  double* xw;
-  int* sync;        // [0] claim counter; per chunk c: flags at 32 + c*stride, node counters after the flags
-  int ntasks, nrhs, nchunk, stride, nstrips;
-};
 
 template <int RC, bool FWD>
-__global__ void __launch_bounds__(PT, RC == 1 ? 2 : 1) k_solve_pipe(const PipeArgs a) {
-  extern __shared__ __align__(16) double sm[];
+__global__ void __launch_bounds__(PT, RC == 1 ? 2 : 1) k_solve_pipe(const __grid_constant__ PipeArgs a) {
   __shared__ int s_next;
+  __shared__ PTask s_tk;
+  __shared__ PNode s_nd;
   Ctx c;
-  c.arena = a.arena;
-  c.index = a.index;
-  c.xw = a.xw;
-  c.nrhs = a.nrhs;
-  c.Ls = sm;
-  c.red = sm + PS * PSL;
-  c.ys = c.red + PWARPS * PS * RC;
   const int tid = threadIdx.x;
   const int total = a.ntasks * a.nchunk;
   if (tid == 0) s_next = atomicAdd(a.sync, 1);
   __syncthreads();
   int t = s_next;
   while (t < total) {
-    __syncthreads();   // everybody has read s_next
-    int nxt = 0;
-    if (tid == 0) nxt = atomicAdd(a.sync, 1);   // claimed early, consumed after this task
     const int ti = t / a.nchunk, ch = t - ti * a.nchunk;
-    const PTask tk = a.tasks[ti];
-    const PNode nd = a.nodes[tk.node];
+    int nxt = 0;
+    if (tid == 0) {
+      nxt = atomicAdd(a.sync, 1);   // claimed early, consumed after this task
+      s_tk = a.tasks[ti];
+      s_nd = a.nodes[s_tk.node];
+    }
+    __syncthreads();   // descriptors visible; everybody has read s_next
+    const PTask& tk = s_tk;
+    const PNode& nd = s_nd;
     c.rc0 = ch * RC;
     c.nr = min(RC, a.nrhs - c.rc0);
     c.flags = a.sync + 32 + (i64)ch * a.stride;
-    c.cnt = c.flags + a.nstrips;
+    c.cnt = c.flags + (FWD ? 1 : 2) * a.nstrips;   // forward: per-strip counters; backward: per-node counters
+    c.tr = a.trace ? a.trace + 8 * (i64)t : nullptr;
+    if (c.tr && tid == 0) c.tr[0] = c.tr[1] = c.tr[2] = gtime();
     // rows below the diagonal block handled by this task (none for a DIAG task)
     const int rb0 = tk.kind == P_BELOW ? tk.r0 : nd.n;
     const int rb1 = tk.kind == P_BELOW ? tk.r0 + tk.nrows : (tk.kind == P_SMALL ? nd.m : nd.n);
+    const bool fat = nd.np <= FAT_NP;
+    if (rb1 > rb0 && !(a.mode & M_NO_PREFETCH))
+      prefetch_l2(a.arena + nd.off + (i64)rb0 * nd.ld, nd.ld, rb1 - rb0, nd.n);
     if (FWD) {
-      if (tk.kind != P_BELOW) fwd_strip<RC>(nd, tk.node, tk.kind == P_DIAG ? tk.r0 : 0, c);
+      // a SMALL node's x is only read by its own rows below: no flag needed in the forward sweep
+      if (tk.kind != P_BELOW) fwd_strip<RC>(nd, tk.node, tk.kind == P_DIAG ? tk.r0 : 0, tk.kind == P_DIAG, a, c);
       if (tk.kind != P_DIAG) {
-        for (int r = rb0; r < rb1; r += PS) fwd_below<RC>(nd, r, min(PS, rb1 - r), c);
-        bump_dests(a.dest + tk.dest_begin, tk.dest_count, c.cnt);
+        if (fat)
+          fwd_below_fat<RC>(nd, rb0, rb1 - rb0, tk.kind == P_SMALL, a, c);
+        else
+          fwd_below<RC>(nd, rb0, rb1 - rb0, a, c);
+        if (c.tr && tid == 0 && tk.kind == P_BELOW) c.tr[2] = gtime();
+        bump_dests(a.dest + tk.dest_begin, tk.dest_count, c.cnt, a.mode);
       }
     } else {
       if (tk.kind != P_DIAG) {
-        if (tid == 0 && nd.pflag >= 0) wait_count(c.flags + nd.pflag, 1);   // parent (hence every ancestor) done
-        for (int r = rb0; r < rb1; r += PS) bwd_below<RC>(nd, r, min(PS, rb1 - r), c);
-        __threadfence();
+        // every ancestor strip this task's rows map to has published its x
+        for (int k = tid; k < tk.dest_count; k += PT) wait_count(c.flags + a.dest[tk.dest_begin + k], 1, a.mode);
+        bwd_below<RC>(nd, rb0, rb1 - rb0, a, c);
+        if (c.tr && tid == 0 && tk.kind == P_BELOW) c.tr[2] = gtime();
+        if (tk.kind == P_SMALL) fence_gpu(a.mode);   // own REDs, re-read by this CTA right below
         __syncthreads();
-        if (tk.kind == P_BELOW && tid == 0) atomicAdd(c.cnt + tk.node, 1);
+        if (tk.kind == P_BELOW && tid == 0) {
+          fence_gpu(a.mode);
+          atomicAdd(c.cnt + tk.node, 1);
+        }
       }
-      if (tk.kind != P_BELOW) bwd_strip<RC>(nd, tk.node, tk.kind == P_DIAG ? tk.r0 : 0, tk.kind == P_DIAG, c);
+      if (tk.kind != P_BELOW) bwd_strip<RC>(nd, tk.node, tk.kind == P_DIAG ? tk.r0 : 0, tk.kind == P_DIAG, a, c);
     }
     __syncthreads();
+    if (c.tr && tid == 0) c.tr[3] = gtime();
     if (tid == 0) s_next = nxt;
     __syncthreads();
     t = s_next;
   }
 }
 
-static int pipe_smem(int rc) { return (PS * PSL + PWARPS * PS * rc + PS * rc) * (int)sizeof(double); }
+// ------------------------------------------------------------------------------ diagonal inverses
+// One CTA per strip: the 64 x 64 (or narrower) lower-triangular diagonal block L_ii of the factor
+// is inverted by forward substitution, thread c computing column c of L_ii^-1.  Runs once per
+// factorization; the solves then replace the latency-bound substitution (a13 slv_solve: dtrsv /
+// dtrsm on the diagonal tile) by a 64 x 64 matrix-vector product.
+__global__ void __launch_bounds__(PS) k_invert_diag(const PNode* __restrict__ nodes, const int* __restrict__ strip_node,
+                                                    const double* __restrict__ arena, double* __restrict__ dinv) {
+  extern __shared__ __align__(16) double ism[];
+  double* Ls = ism;
+  double* Y = ism + PS * PSL;
+  double* rd = Y + PS * PSL;
+  const int strip = blockIdx.x, c = threadIdx.x;
+  const PNode nd = nodes[strip_node[strip]];
+  const int i = strip - nd.strip0, r0 = i * PS, rw = min(PS, nd.n - r0);
+  const double* D = arena + nd.off + (i64)r0 * nd.ld + r0;
+  for (int idx = c; idx < PS * PS; idx += PS) {
+    const int r = idx >> 6, cc = idx & (PS - 1);
+    Ls[r * PSL + cc] = (r < rw && cc <= r) ? D[(i64)r * nd.ld + cc] : 0.0;
+  }
+  __syncthreads();
+  {
+    const double d = c < rw ? Ls[c * PSL + c] : 0.0;
+    rd[c] = d != 0.0 ? 1.0 / d : 0.0;
+  }
+  __syncthreads();
+  // column c of the inverse: y_r = (delta_rc - sum_{k<r} L[r][k] y_k) / L[r][r]; y_k = 0 for k < c
+  for (int r = 0; r < rw; ++r) {
+    double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = c & ~3;   // rows above c hold zeros; every thread only reads its own column of Y
+    for (; k + 3 < r; k += 4) {
+      s0 = fma(-Ls[r * PSL + k], Y[k * PSL + c], s0);
+      s1 = fma(-Ls[r * PSL + k + 1], Y[(k + 1) * PSL + c], s1);
+      s2 = fma(-Ls[r * PSL + k + 2], Y[(k + 2) * PSL + c], s2);
+      s3 = fma(-Ls[r * PSL + k + 3], Y[(k + 3) * PSL + c], s3);
+    }
+    for (; k < r; ++k) s0 = fma(-Ls[r * PSL + k], Y[k * PSL + c], s0);
+    Y[r * PSL + c] = (r >= c) ? ((s0 + s1) + (s2 + s3)) * rd[r] : 0.0;
+  }
+  for (int r = rw; r < PS; ++r) Y[r * PSL + c] = 0.0;
+  __syncthreads();
+  double* out = dinv + (i64)strip * (PS * PS);
+  for (int idx = c; idx < PS * PS; idx += PS) out[idx] = Y[(idx >> 6) * PSL + (idx & (PS - 1))];
+}
+
+constexpr int INVERT_SMEM = (2 * PS * PSL + PS) * (int)sizeof(double);
+void launch_invert_diag(const PNode* nodes, const int* strip_node, int nstrips, const double* arena, double* dinv,
+                        cudaStream_t st) {
+  if (nstrips <= 0) return;
+  k_invert_diag<<<nstrips, PS, INVERT_SMEM, st>>>(nodes, strip_node, arena, dinv);
+}
+
+static int pipe_smem(int rc) { return (rc == 1 ? Sm<1>::TOTAL : Sm<PIPE_RC>::TOTAL) * (int)sizeof(double); }
 static int g_pipe_grid[2][2] = {{0, 0}, {0, 0}};   // [rc index][fwd] resident CTAs on the whole device
 
 template <int RC, bool FWD>
@@ -507,6 +764,7 @@ static int pipe_prepare() {
 }
 
 void pipe_init() {
+  CK(cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, INVERT_SMEM));
   g_pipe_grid[0][1] = pipe_prepare<1, true>();
   g_pipe_grid[0][0] = pipe_prepare<1, false>();
   g_pipe_grid[1][1] = pipe_prepare<PIPE_RC, true>();
@@ -519,15 +777,18 @@ i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs) {
   return 32 + (i64)pipe_chunks(nrhs) * pipe_sync_stride(nstrips, nnodes);
 }
 
-void launch_solve_pipe(bool fwd, const PTask* tasks, int ntasks, const PNode* nodes, const int* dest,
-                       const double* arena, const int* index, double* xw, int nrhs, int nstrips, int nnodes,
-                       int* sync, cudaStream_t st) {
+void launch_solve_pipe(bool fwd, const PTask* tasks, int ntasks, const PNode* nodes, const int* dest, const int* expect,
+                       const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
+                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace) {
   if (ntasks <= 0) return;
+  const int mode = getenv("SPLLT_B200_PIPE_MODE") ? atoi(getenv("SPLLT_B200_PIPE_MODE")) : 0;
   PipeArgs a;
   a.tasks = tasks;
   a.nodes = nodes;
   a.dest = dest;
+  a.expect = expect;
   a.arena = arena;
+  a.dinv = dinv;
   a.index = index;
   a.xw = xw;
   a.sync = sync;
@@ -536,6 +797,8 @@ void launch_solve_pipe(bool fwd, const PTask* tasks, int ntasks, const PNode* no
   a.nchunk = pipe_chunks(nrhs);
   a.stride = pipe_sync_stride(nstrips, nnodes);
   a.nstrips = nstrips;
+  a.mode = mode;
+  a.trace = trace;
   CK(cudaMemsetAsync(sync, 0, pipe_sync_ints(nstrips, nnodes, nrhs) * sizeof(int), st));
   const i64 total = (i64)ntasks * a.nchunk;
   const int rci = nrhs == 1 ? 0 : 1;

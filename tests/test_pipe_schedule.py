@@ -38,7 +38,7 @@ def tables(case):
 @pytest.mark.parametrize("case", CASES, ids=ids(CASES))
 def test_lists_are_topological_and_cover(case):
     s, (n, ptr, row, val), (sptr, sparent, rptr, rlist) = tables(case)
-    tf, tb, nd, dest, nstrips = s.pipe_tables()
+    tf, tb, nd, dest, nstrips, expect = s.pipe_tables()
     nn = s.nnodes
     m_, n_, sa, strip0, np_, exp_f, exp_b, pflag = nd.T
     assert np.array_equal(n_, np.diff(sptr)) and np.array_equal(m_, np.diff(rptr))
@@ -46,62 +46,63 @@ def test_lists_are_topological_and_cover(case):
     assert np.array_equal(np_, (n_ + PS - 1) // PS)
     assert np.array_equal(strip0, np.concatenate([[0], np.cumsum(np_)[:-1]])) and nstrips == np_.sum()
     col2node = np.repeat(np.arange(nn), n_)
+    col2strip = strip0[col2node] + (np.arange(n) - sa[col2node]) // PS     # pivot column -> global strip
     idx = [rlist[rptr[k] - 1:rptr[k + 1] - 1] - 1 for k in range(nn)]
-    for k in range(nn):
-        p = sparent[k] - 1
-        assert pflag[k] == (strip0[p] if p < nn else -1)
 
-    # ---- forward
+    def strips_of(k, r0, r1):
+        st = col2strip[idx[k][r0:r1]]
+        return st[np.concatenate([[True], np.diff(st) != 0])] if len(st) else st
+
+    # ---- forward: a strip reads its right-hand side only after every task that adds into its
+    # rows has finished (counter == expect at that moment), and waits only on earlier tasks
     flags = np.zeros(nstrips, bool)
-    cnt = np.zeros(nn, np.int64)
+    cnt = np.zeros(nstrips, np.int64)
     rows_done = [np.zeros(m_[k], np.int32) for k in range(nn)]
 
     def fwd_below(k, r0, r1, db, dc):
-        assert flags[strip0[k]:strip0[k] + np_[k]].all()          # waits only on earlier tasks
-        want = col2node[idx[k][r0:r1]]
-        want = want[np.concatenate([[True], np.diff(want) != 0])] if len(want) else want
+        assert flags[strip0[k]:strip0[k] + np_[k]].all()          # x of the node is complete
+        want = strips_of(k, r0, r1)
         assert np.array_equal(dest[db:db + dc], want)
-        for d in want:
-            assert not flags[strip0[d]]                            # lands before the ancestor reads
-            cnt[d] += 1
+        assert not flags[want].any()                              # lands before the ancestor strip reads
+        cnt[want] += 1
         rows_done[k][r0:r1] += 1
 
     for node, kind, r0, nrows, db, dc in tf:
         if kind in (DIAG, SMALLK):
             i = r0 if kind == DIAG else 0
-            assert flags[strip0[node]:strip0[node] + i].all() and not flags[strip0[node] + i]
-            if i == 0:
-                assert cnt[node] == exp_f[node]
-            flags[strip0[node] + i] = True
+            f = strip0[node] + i
+            assert flags[strip0[node]:f].all() and not flags[f]
+            assert cnt[f] == expect[f]
+            flags[f] = True
             rows_done[node][i * PS:min((i + 1) * PS, n_[node])] += 1
             if kind == SMALLK:
                 assert np_[node] == 1
                 fwd_below(node, n_[node], m_[node], db, dc)
         else:
-            assert r0 >= n_[node] and 0 < nrows <= PS
+            assert r0 >= n_[node] and 0 < nrows <= (512 if np_[node] <= 4 else PS)
             fwd_below(node, r0, r0 + nrows, db, dc)
-    assert flags.all() and np.array_equal(cnt, exp_f)
+    assert flags.all() and np.array_equal(cnt, expect)
     assert all((r == 1).all() for r in rows_done)
 
-    # ---- backward
+    # ---- backward: a below task gathers x only from strips that are already published
     flags[:] = False
     cntb = np.zeros(nn, np.int64)
     rows_done = [np.zeros(m_[k], np.int32) for k in range(nn)]
 
-    def bwd_below(k, r0, r1):
-        assert pflag[k] < 0 or flags[pflag[k]]
-        for d in np.unique(col2node[idx[k][r0:r1]]):
-            assert flags[strip0[d]:strip0[d] + np_[d]].all()       # every ancestor touched is complete
+    def bwd_below(k, r0, r1, db, dc):
+        want = strips_of(k, r0, r1)
+        assert np.array_equal(dest[db:db + dc], want)
+        assert flags[want].all()
         assert not flags[strip0[k]:strip0[k] + np_[k]].any()
         rows_done[k][r0:r1] += 1
 
     for node, kind, r0, nrows, db, dc in tb:
         if kind == BELOW:
-            bwd_below(node, r0, r0 + nrows)
+            bwd_below(node, r0, r0 + nrows, db, dc)
             cntb[node] += 1
             continue
         if kind == SMALLK:
-            bwd_below(node, n_[node], m_[node])
+            bwd_below(node, n_[node], m_[node], db, dc)
             i = 0
         else:
             i = r0
@@ -125,7 +126,7 @@ def test_lists_replayed_numerically(case):
     kernels (strip gathers, below-row scatters with counters, transposed gathers)."""
     s, (n, ptr, row, val), (sptr, sparent, rptr, rlist) = tables(case)
     name, mk, nb, ncpu, prune = case
-    tf, tb, nd, dest, nstrips = s.pipe_tables()
+    tf, tb, nd, dest, nstrips, expect = s.pipe_tables()
     nn = s.nnodes
     m_, n_, sa, strip0, np_, exp_f, exp_b, pflag = nd.T
     o = Oracle(n, ptr, row, s.order, sptr, sparent, rptr, rlist, nb, ncpu=ncpu, prune=prune)
