@@ -765,8 +765,9 @@ static void build_pipe_schedule(Analysis& A) {
     if (!is_small0(A.nodes[s]) && A.pnodes[s].np <= PIPE_FAT_NP) below_rows[A.nodes[s].depth0] += A.nodes[s].m - A.nodes[s].n;
   auto chunk_of = [&](int s) {
     if (A.pnodes[s].np > PIPE_FAT_NP) return PS;
-    i64 c = (below_rows[A.nodes[s].depth0] / PIPE_LEVEL_TASKS + PS - 1) / PS * PS;
-    return (int)std::max<i64>(PS, std::min<i64>(PIPE_FAT_ROWS, c));
+    const i64 by_level = (below_rows[A.nodes[s].depth0] / PIPE_LEVEL_TASKS + PS - 1) / PS * PS;
+    const i64 by_bytes = (PIPE_TASK_BYTES / (8 * (i64)A.nodes[s].n) + PS - 1) / PS * PS;   // enough bytes per task
+    return (int)std::max<i64>(PS, std::min<i64>(PIPE_FAT_ROWS, std::max(by_level, by_bytes)));
   };
   auto is_small = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
   for (int s : ord) {
@@ -778,11 +779,15 @@ static void build_pipe_schedule(Analysis& A) {
       continue;
     }
     for (int i = 0; i < A.pnodes[s].np; ++i) A.ptasks_f.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
+    // the first 64 rows are their own task: they feed the parent's first strip (forward) and are
+    // the last to become ready (backward), i.e. they sit on the critical path of a chain of nodes
     const int chunk = chunk_of(s);
-    for (int r = nd.n; r < nd.m; r += chunk) {
-      PTask t{s, P_BELOW, r, std::min(chunk, nd.m - r), 0, 0, {0, 0}};
+    for (int r = nd.n; r < nd.m;) {
+      const int rows = std::min(r == nd.n ? PS : chunk, nd.m - r);
+      PTask t{s, P_BELOW, r, rows, 0, 0, {0, 0}};
       dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
       A.ptasks_f.push_back(t);
+      r += rows;
     }
   }
   // the backward tasks reuse the forward tasks' strip lists (same row ranges)
@@ -816,35 +821,45 @@ void build_solve_schedule(Analysis& A) {
     const char* l = getenv("SPLLT_B200_SOLVE_LEVELSET");
     if (l && atoi(l)) A.solve_cut = 1 << 30;
   }
+  {
+    const char* e = getenv("SPLLT_B200_PIPE_MAX_NRHS");
+    A.pipe_max_nrhs = e ? atoi(e) : 8;
+  }
   A.sbcols.clear();
   A.supds.clear();
-  A.slaunch.assign(A.ndepth, SolveLaunch{0, 0, 0, 0});
-  std::vector<std::vector<int>> at(A.ndepth);
-  for (int s = 0; s < nn; ++s)
-    if (A.nodes[s].depth0 < A.solve_cut)
-      for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
-  for (int d = 0; d < A.ndepth; ++d) {
-    SolveLaunch& L = A.slaunch[d];
-    L.diag_begin = A.sbcols.size();
-    L.upd_begin = A.supds.size();
-    for (int g : at[d]) {
-      const HNode& nd = A.nodes[A.bcol_node[g]];
-      SolveBcol b;
-      b.off = nd.off;
-      b.idx_off = nd.idx_off;
-      b.ld = nd.ld;
-      b.m = nd.m;
-      b.r0 = A.bcol_c[g] * nb;
-      b.w = std::min(nb, nd.n - b.r0);
-      b.sa = nd.sa;
-      b.pad = 0;
-      int id = (int)A.sbcols.size();
-      A.sbcols.push_back(b);
-      for (int r = b.r0 + b.w; r < nd.m; r += SOLVE_ROWS)
-        A.supds.push_back({id, r, std::min(SOLVE_ROWS, nd.m - r), 0});
+  // two level-set schedules in the same lists: the nodes below the cut (companion of the
+  // persistent kernels) and all nodes (many right-hand sides)
+  for (int pass = 0; pass < 2; ++pass) {
+    std::vector<SolveLaunch>& SL = pass == 0 ? A.slaunch : A.slaunch_full;
+    const int cut = pass == 0 ? A.solve_cut : (1 << 30);
+    SL.assign(A.ndepth, SolveLaunch{0, 0, 0, 0});
+    std::vector<std::vector<int>> at(A.ndepth);
+    for (int s = 0; s < nn; ++s)
+      if (A.nodes[s].depth0 < cut)
+        for (int c = 0; c < A.nodes[s].nc; ++c) at[A.nodes[s].depth0 + c].push_back(A.nodes[s].bcol0 + c);
+    for (int d = 0; d < A.ndepth; ++d) {
+      SolveLaunch& L = SL[d];
+      L.diag_begin = A.sbcols.size();
+      L.upd_begin = A.supds.size();
+      for (int g : at[d]) {
+        const HNode& nd = A.nodes[A.bcol_node[g]];
+        SolveBcol b;
+        b.off = nd.off;
+        b.idx_off = nd.idx_off;
+        b.ld = nd.ld;
+        b.m = nd.m;
+        b.r0 = A.bcol_c[g] * nb;
+        b.w = std::min(nb, nd.n - b.r0);
+        b.sa = nd.sa;
+        b.pad = 0;
+        int id = (int)A.sbcols.size();
+        A.sbcols.push_back(b);
+        for (int r = b.r0 + b.w; r < nd.m; r += SOLVE_ROWS)
+          A.supds.push_back({id, r, std::min(SOLVE_ROWS, nd.m - r), 0});
+      }
+      L.diag_count = (i64)A.sbcols.size() - L.diag_begin;
+      L.upd_count = (i64)A.supds.size() - L.upd_begin;
     }
-    L.diag_count = (i64)A.sbcols.size() - L.diag_begin;
-    L.upd_count = (i64)A.supds.size() - L.upd_begin;
   }
   build_pipe_schedule(A);
 }

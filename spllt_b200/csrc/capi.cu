@@ -493,12 +493,14 @@ long long spllt_b200_factor_launches(void* fkeep) {
   return (long long)A.launches.size() + 1;  // + assemble (the two memsets are not kernels of ours)
 }
 long long spllt_b200_solve_launches(void* fkeep, int job) {
+  // kernels of one solve with a single right-hand side (the pipelined path when it is enabled)
   const Analysis& A = *EE(fkeep)->A;
+  const bool pipe = EE(fkeep)->use_pipe(1);
   long long per = 0;
-  for (const SolveLaunch& L : A.slaunch) per += (L.diag_count > 0) + (L.upd_count > 0);
-  long long tot = 0;   // level-set launches (below the cut) + persistent kernel + permutation
-  if (job == 0 || job == 1) tot += per + !A.ptasks_f.empty() + 1;
-  if (job == 0 || job == 2) tot += per + !A.ptasks_b.empty() + 1;
+  for (const SolveLaunch& L : (pipe ? A.slaunch : A.slaunch_full)) per += (L.diag_count > 0) + (L.upd_count > 0);
+  long long tot = 0;   // level-set launches + persistent kernel + permutation
+  if (job == 0 || job == 1) tot += per + pipe + 1;
+  if (job == 0 || job == 2) tot += per + pipe + 1;
   return tot;
 }
 double spllt_b200_tile_flops(void* akeep) { return AA(akeep)->tile_flops; }

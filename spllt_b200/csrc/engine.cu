@@ -131,8 +131,16 @@ void Engine::upload_tables() {
   d_sb = upload(S.sbcols);
   d_su = upload(S.supds);
   d_pnodes = upload(S.pnodes);
-  d_ptask_f = upload(S.ptasks_f);
-  d_ptask_b = upload(S.ptasks_b);
+  {
+    std::vector<PTaskD> td;
+    for (int dir = 0; dir < 2; ++dir) {
+      const std::vector<PTask>& src = dir == 0 ? S.ptasks_f : S.ptasks_b;
+      td.clear();
+      td.reserve(src.size());
+      for (const PTask& t : src) td.push_back(PTaskD{t, S.pnodes[t.node]});
+      (dir == 0 ? d_ptask_f : d_ptask_b) = upload(td);
+    }
+  }
   d_pdest = upload(S.pipe_dest);
   d_strip_node = upload(S.strip_node);
   d_pexpect = upload(S.pexpect);
@@ -361,22 +369,28 @@ void Engine::factor_host(const double* val) {
 
 // The sweeps work on the internal pivot-order vector d_xw only, so the captured graph does
 // not depend on the caller's x: the two permutation kernels are launched around it.
+bool Engine::use_pipe(int nrhs) const { return !A->ptasks_f.empty() && nrhs <= A->pipe_max_nrhs; }
+
 void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
   const Analysis& S = *A;
+  const bool pipe = use_pipe(nrhs);
+  const std::vector<SolveLaunch>& SL = pipe ? S.slaunch : S.slaunch_full;
   if (job == 0 || job == 1) {
     for (int d = 0; d < S.ndepth; ++d) {
-      const SolveLaunch& L = S.slaunch[d];
+      const SolveLaunch& L = SL[d];
       launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
       launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
     }
-    launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                      S.nstrips, S.nnodes, d_psync, st);
+    if (pipe)
+      launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+                        S.nstrips, S.nnodes, d_psync, st);
   }
   if (job == 0 || job == 2) {
-    launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                      S.nstrips, S.nnodes, d_psync + psync_ints, st);
+    if (pipe)
+      launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+                        S.nstrips, S.nnodes, d_psync + psync_ints, st);
     for (int d = S.ndepth - 1; d >= 0; --d) {
-      const SolveLaunch& L = S.slaunch[d];
+      const SolveLaunch& L = SL[d];
       launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
       launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
     }
@@ -432,6 +446,8 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
   ensure_solve_buffers(nrhs);
   ensure_dinv();
   const Analysis& S = *A;
+  const bool pipe = use_pipe(nrhs);
+  const std::vector<SolveLaunch>& SL = pipe ? S.slaunch : S.slaunch_full;
   cudaStream_t st = stream;
   struct Rec {
     int kind, depth;
@@ -448,7 +464,7 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
   launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
   mark();
   for (int d = 0; d < S.ndepth; ++d) {
-    const SolveLaunch& L = S.slaunch[d];
+    const SolveLaunch& L = SL[d];
     if (L.diag_count == 0 && L.upd_count == 0) continue;
     launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
     mark();
@@ -457,16 +473,18 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
     mark();
     recs.push_back({1, d, L.upd_count});
   }
-  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
+  if (pipe) {
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
                     S.nnodes, d_psync, st);
   mark();
   recs.push_back({4, -1, (long long)S.ptasks_f.size()});
-  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
                     S.nstrips, S.nnodes, d_psync + psync_ints, st);
   mark();
   recs.push_back({5, -1, (long long)S.ptasks_b.size()});
+  }
   for (int d = S.ndepth - 1; d >= 0; --d) {
-    const SolveLaunch& L = S.slaunch[d];
+    const SolveLaunch& L = SL[d];
     if (L.diag_count == 0 && L.upd_count == 0) continue;
     launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
     mark();
@@ -510,9 +528,9 @@ void Engine::trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_
     launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, stream);
     launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
   }
-  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
                     S.nnodes, d_psync, stream, tf);
-  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pnodes, d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
                     S.nstrips, S.nnodes, d_psync + psync_ints, stream, tb);
   for (int d = S.ndepth - 1; d >= 0; --d) {
     const SolveLaunch& L = S.slaunch[d];

@@ -54,8 +54,8 @@ struct Engine {
   SolveBcol* d_sb = nullptr;
   SolveUpd* d_su = nullptr;
   PNode* d_pnodes = nullptr;      // pipelined solve tables (solve_pipe.cu)
-  PTask* d_ptask_f = nullptr;
-  PTask* d_ptask_b = nullptr;
+  PTaskD* d_ptask_f = nullptr;    // task + node records, forward / backward order
+  PTaskD* d_ptask_b = nullptr;
   int* d_pdest = nullptr;
   int* d_strip_node = nullptr;
   int* d_pexpect = nullptr;
@@ -87,6 +87,7 @@ struct Engine {
   void launch_one(const Launch& L, cudaStream_t st, bool background);
   void enqueue_solve(int nrhs, int job, cudaStream_t st);
   void ensure_dinv();
+  bool use_pipe(int nrhs) const;   // persistent pipelined kernels (few right-hand sides) or level-set launches
   void solve(double* dx, int ldx, int nrhs, int job);
   void profile_solve(double* dx, int ldx, int nrhs, double* ms6, const char* csv);
   void trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_f, unsigned long long* out_b);

@@ -124,6 +124,7 @@ constexpr int PIPE_SMALL_ROWS = 256;  // nodes with n <= PS and m - n <= this ar
 constexpr int PIPE_FAT_NP = 4;        // nodes with at most this many strips: rows below them are streamed in
 constexpr int PIPE_FAT_ROWS = 512;    //   chunks of up to this many rows after the whole node is solved
 constexpr int PIPE_LEVEL_TASKS = 512; // ... sized so that a tree level yields about this many chunks
+constexpr int PIPE_TASK_BYTES = 128 * 1024;  // ... and a chunk streams at least this many bytes of L
 enum PipeKind { P_DIAG = 0, P_BELOW = 1, P_SMALL = 2 };
 struct PNode {
   i64 off;           // arena offset of the node
@@ -142,6 +143,11 @@ struct PTask {
   int dest_begin, dest_count;  // ancestor strips its rows map to (pipe_dest): forward = counters it bumps,
                                // backward = flags it waits for
   int pad[2];
+};
+
+struct PTaskD {      // what the kernels read: task + its node in ONE 96-byte record (one load per claim)
+  PTask t;
+  PNode n;
 };
 
 // ------------------------------------------------------------------ reference-format tables
@@ -196,7 +202,9 @@ struct Analysis {
   // solve schedule (forward order; the backward sweep walks it in reverse)
   std::vector<SolveBcol> sbcols;
   std::vector<SolveUpd> supds;
-  std::vector<SolveLaunch> slaunch;   // one per depth
+  std::vector<SolveLaunch> slaunch;   // one per depth: nodes below solve_cut (none by default)
+  std::vector<SolveLaunch> slaunch_full;  // one per depth: ALL nodes (used when nrhs > pipe_max_nrhs)
+  int pipe_max_nrhs = 8;              // more right-hand sides than this: level-set launches (RC = 8 kernels)
   // pipelined solve: nodes with depth0 >= solve_cut run in the persistent kernels, the rest
   // (none by default) in the level-set launches above
   int solve_cut = 0;

@@ -51,6 +51,9 @@ constexpr int PT = 256;            // threads per CTA
 constexpr int PWARPS = PT / 32;    // 8
 constexpr int RPW = PS / PWARPS;   // 8 rows of a strip per warp
 constexpr int PSL = PS + 1;        // padded leading dimension of the diagonal block in shared memory
+#ifndef PIPE_OCC
+#define PIPE_OCC 3   // resident CTAs per SM of the single-rhs kernels (register cap 85)
+#endif
 constexpr int FAT_NP = PIPE_FAT_NP;
 constexpr int PREFETCH_BYTES = 128 * 1024;   // per task
 static_assert(PS * PIPE_RC <= PT, "one right-hand-side entry of a strip per thread");
@@ -152,8 +155,7 @@ __device__ __forceinline__ void wait_count(const int* c, int expect, int mode) {
 }
 
 struct PipeArgs {
-  const PTask* tasks;
-  const PNode* nodes;
+  const PTaskD* tasks;
   const int* dest;
   const int* expect;   // [nstrips] forward: contributions a strip waits for
   const double* arena;
@@ -628,10 +630,10 @@ __device__ __forceinline__ void bwd_below(const PNode& nd, int r0, int nrows, co
 
 
 template <int RC, bool FWD>
-__global__ void __launch_bounds__(PT, RC == 1 ? 2 : 1) k_solve_pipe(const __grid_constant__ PipeArgs a) {
+__global__ void __launch_bounds__(PT, RC == 1 ? PIPE_OCC : 1) k_solve_pipe(const __grid_constant__ PipeArgs a) {
   __shared__ int s_next;
-  __shared__ PTask s_tk;
-  __shared__ PNode s_nd;
+  __shared__ PTaskD s_td;
+  static_assert(sizeof(PTaskD) == 96, "PTaskD is copied as 24 ints");
   Ctx c;
   const int tid = threadIdx.x;
   const int total = a.ntasks * a.nchunk;
@@ -641,14 +643,11 @@ __global__ void __launch_bounds__(PT, RC == 1 ? 2 : 1) k_solve_pipe(const __grid
   while (t < total) {
     const int ti = t / a.nchunk, ch = t - ti * a.nchunk;
     int nxt = 0;
-    if (tid == 0) {
-      nxt = atomicAdd(a.sync, 1);   // claimed early, consumed after this task
-      s_tk = a.tasks[ti];
-      s_nd = a.nodes[s_tk.node];
-    }
-    __syncthreads();   // descriptors visible; everybody has read s_next
-    const PTask& tk = s_tk;
-    const PNode& nd = s_nd;
+    if (tid == 0) nxt = atomicAdd(a.sync, 1);   // claimed early, consumed after this task
+    if (tid < 24) ((int*)&s_td)[tid] = ((const int*)(a.tasks + ti))[tid];
+    __syncthreads();   // descriptor visible; everybody has read s_next
+    const PTask& tk = s_td.t;
+    const PNode& nd = s_td.n;
     c.rc0 = ch * RC;
     c.nr = min(RC, a.nrhs - c.rc0);
     c.flags = a.sync + 32 + (i64)ch * a.stride;
@@ -777,14 +776,13 @@ i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs) {
   return 32 + (i64)pipe_chunks(nrhs) * pipe_sync_stride(nstrips, nnodes);
 }
 
-void launch_solve_pipe(bool fwd, const PTask* tasks, int ntasks, const PNode* nodes, const int* dest, const int* expect,
+void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* dest, const int* expect,
                        const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
                        int nnodes, int* sync, cudaStream_t st, unsigned long long* trace) {
   if (ntasks <= 0) return;
   const int mode = getenv("SPLLT_B200_PIPE_MODE") ? atoi(getenv("SPLLT_B200_PIPE_MODE")) : 0;
   PipeArgs a;
   a.tasks = tasks;
-  a.nodes = nodes;
   a.dest = dest;
   a.expect = expect;
   a.arena = arena;

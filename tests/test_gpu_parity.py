@@ -349,6 +349,27 @@ def test_solve_variants(case, env, nrhs, monkeypatch):
     assert np.max(np.abs(x2 - xo)) <= 1e-10 * np.abs(xo).max()
 
 
+@pytest.mark.parametrize("case", [SMALL[11], MEDIUM[1], MEDIUM[3]], ids=ids([SMALL[11], MEDIUM[1], MEDIUM[3]]))
+@pytest.mark.parametrize("nrhs", [9, 19])
+def test_pipelined_solve_many_rhs(case, nrhs, monkeypatch):
+    """By default more than 8 right-hand sides go to the level-set kernels; forced through the
+    persistent kernels (several passes of 4 right-hand sides, the last one partial) the result
+    is the same."""
+    monkeypatch.setenv("SPLLT_B200_PIPE_MAX_NRHS", "64")
+    s, o, mat = both(case)
+    n, ptr, row, val = mat
+    xs, b = rhs_for(mat, nrhs, seed=5)
+    s.prepare_solve(nrhs)
+    o.prepare_solve(nrhs)
+    xo = b.copy(order="F")
+    o.solve(xo, 0)
+    x = b.copy(order="F")
+    assert s.solve(x, 0) == 0
+    ok, err = chkerr(n, ptr, row, val, x, b)
+    assert ok == nrhs and err.max() <= BWD_TOL
+    assert np.max(np.abs(x - xo)) <= 1e-10 * np.abs(xo).max()
+
+
 def test_unsorted_input_columns():
     """Entries of a column may come in any order; the A -> L map follows the input order."""
     n, ptr, row, val = M.poisson3d(8)
