@@ -285,7 +285,11 @@ def main():
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         solve = {"nrhs": nrhs, "seconds": ms_solve / 1e3, "seconds_per_rhs": ms_solve / 1e3 / nrhs,
                  "algorithmic_bytes": sbytes, "achieved_gbs": sbytes / ms_solve / 1e6, "hbm_peak_gbs": hbm_peak,
-                 "frac_of_hbm": sbytes / ms_solve / 1e6 / hbm_peak, "launches": int(L.spllt_b200_solve_launches(s.fkeep, 0))}
+                 "frac_of_hbm": sbytes / ms_solve / 1e6 / hbm_peak, "launches": int(L.spllt_b200_solve_launches(s.fkeep, 0)),
+                 "path": ("persistent pipelined kernels k_solve_pipe<fwd>/<bwd> (64-row strips, flags in HBM)"
+                          if nrhs <= 8 and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET") else
+                          "level-set launches k_fwd_diag/k_fwd_upd/k_bwd_upd/k_bwd_diag"),
+                 "profile_ms": s.profile_solve(d_rhs[0].data_ptr(), nrhs)}
         parity = {"scaled_backward_error_max": float(err.max()), "rhs_ok": int(ok), "nrhs": nrhs, "tol": 1e-14,
                   "forward_error_max": float(np.abs(x - xs).max() / np.abs(xs).max()), "pivot_flag": int(pivot)}
 

@@ -97,3 +97,20 @@ for name, tr, tasks in (('fwd', f, tf), ('bwd', bk, tb)):
         if len(B):
             line += ' | B %3d %8.1f %8.1f  stream med %.1f  %8.1f' % (len(B), B[:, 0].min(), B[:, 1].min(), np.median(B[:, 2] - B[:, 1]), B[:, 3].max())
         print(line)
+
+# ---- who delivers the last contribution to a chain node's first strip (forward)?
+tr = f.astype(np.int64); tr = (tr - tr[:, 0].min()) / 1e3
+strip0 = nd[:, 3]
+print('late contributors (fwd): for chain nodes, tasks whose dest list holds the node strip 0')
+for k in path[3:12]:
+    s0 = strip0[k]
+    rows = []
+    for ti, (node, kind, r0, nrows, db, dc) in enumerate(tf):
+        if kind != 0 and dc > 0 and s0 in de[db:db + dc]:
+            rows.append((tr[ti, 3], node, kind, r0, nrows, tr[ti, 0], tr[ti, 1], tr[ti, 2]))
+    rows.sort()
+    md = (tf[:, 0] == k) & (tf[:, 1] != 1)
+    print('  node n=%d m=%d expect %d: D(0) waits-done %.1f' % (nd[k, 1], nd[k, 0], _ex[s0], tr[md][:, 1].min()))
+    for r in rows[-4:]:
+        print('      end %.1f  from node n=%d m=%d kind %d r0 %d nrows %d | start %.1f waits-done %.1f streamed %.1f'
+              % (r[0], nd[r[1], 1], nd[r[1], 0], r[2], r[3], r[4], r[5], r[6], r[7]))

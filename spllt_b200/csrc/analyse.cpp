@@ -763,10 +763,12 @@ static void build_pipe_schedule(Analysis& A) {
   auto is_small0 = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
   for (int s : ord)
     if (!is_small0(A.nodes[s]) && A.pnodes[s].np <= PIPE_FAT_NP) below_rows[A.nodes[s].depth0] += A.nodes[s].m - A.nodes[s].n;
+  const i64 level_tasks = getenv("SPLLT_B200_PIPE_LEVEL_TASKS") ? atoi(getenv("SPLLT_B200_PIPE_LEVEL_TASKS")) : PIPE_LEVEL_TASKS;
+  const i64 task_bytes = getenv("SPLLT_B200_PIPE_TASK_KB") ? 1024 * (i64)atoi(getenv("SPLLT_B200_PIPE_TASK_KB")) : PIPE_TASK_BYTES;
   auto chunk_of = [&](int s) {
     if (A.pnodes[s].np > PIPE_FAT_NP) return PS;
-    const i64 by_level = (below_rows[A.nodes[s].depth0] / PIPE_LEVEL_TASKS + PS - 1) / PS * PS;
-    const i64 by_bytes = (PIPE_TASK_BYTES / (8 * (i64)A.nodes[s].n) + PS - 1) / PS * PS;   // enough bytes per task
+    const i64 by_level = (below_rows[A.nodes[s].depth0] / std::max<i64>(level_tasks, 1) + PS - 1) / PS * PS;
+    const i64 by_bytes = (task_bytes / (8 * (i64)A.nodes[s].n) + PS - 1) / PS * PS;   // enough bytes per task
     return (int)std::max<i64>(PS, std::min<i64>(PIPE_FAT_ROWS, std::max(by_level, by_bytes)));
   };
   auto is_small = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };

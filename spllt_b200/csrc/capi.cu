@@ -490,7 +490,8 @@ int spllt_b200_pivot_flag(void* fkeep) { return EE(fkeep)->pivot_flag(); }
 
 long long spllt_b200_factor_launches(void* fkeep) {
   const Analysis& A = *EE(fkeep)->A;
-  return (long long)A.launches.size() + 1;  // + assemble (the two memsets are not kernels of ours)
+  // + assemble + inversion of the diagonal blocks (the memsets are not kernels of ours)
+  return (long long)A.launches.size() + 2;
 }
 long long spllt_b200_solve_launches(void* fkeep, int job) {
   // kernels of one solve with a single right-hand side (the pipelined path when it is enabled)

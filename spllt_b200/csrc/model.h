@@ -124,7 +124,7 @@ constexpr int PIPE_SMALL_ROWS = 256;  // nodes with n <= PS and m - n <= this ar
 constexpr int PIPE_FAT_NP = 4;        // nodes with at most this many strips: rows below them are streamed in
 constexpr int PIPE_FAT_ROWS = 512;    //   chunks of up to this many rows after the whole node is solved
 constexpr int PIPE_LEVEL_TASKS = 512; // ... sized so that a tree level yields about this many chunks
-constexpr int PIPE_TASK_BYTES = 128 * 1024;  // ... and a chunk streams at least this many bytes of L
+constexpr int PIPE_TASK_BYTES = 64 * 1024;  // ... and a chunk streams at least this many bytes of L
 enum PipeKind { P_DIAG = 0, P_BELOW = 1, P_SMALL = 2 };
 struct PNode {
   i64 off;           // arena offset of the node
