@@ -125,6 +125,13 @@ void spllt_b200_bcol_region(void *akeep, int node, int c, long long *off, int *l
 void spllt_b200_pack_bcol(void *akeep, void *fkeep, int node, int c, double *d_buf);
 void spllt_b200_unpack_bcol(void *akeep, void *fkeep, int node, int c, const double *d_buf);
 int spllt_b200_dist_top(void *akeep);
+/* multi-GPU solve, one call per phase (all asynchronous on the stream).  The caller sums the work
+ * vector (spllt_b200_xw_ptr: n x nrhs doubles, row-major) over the ranks after phases 1 and 4.
+ * 0: permute the rhs in, drop the entries this rank does not own; 1: forward sweep of the rank's
+ * subtrees; 2: forward sweep of the upper tree; 3: backward sweep of the upper tree; 4: backward
+ * sweep of the rank's subtrees, drop foreign entries; 5: permute the solution out (d_x, ldx). */
+void spllt_b200_solve_phase(void *fkeep, int nrhs, double *d_x, int ldx, int phase);
+void *spllt_b200_xw_ptr(void *fkeep, int nrhs);
 /* phase 0 = assemble + local subtrees, phase 1 = shared top; both asynchronous */
 void spllt_b200_factor_phase(void *akeep, void *fkeep, const double *d_val, int phase);
 

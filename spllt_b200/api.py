@@ -125,6 +125,8 @@ def load_library(path=None):
         "spllt_b200_pack_bcol": (None, [vp, vp, C.c_int, C.c_int, vp]),
         "spllt_b200_unpack_bcol": (None, [vp, vp, C.c_int, C.c_int, vp]),
         "spllt_b200_dist_top": (C.c_int, [vp]),
+        "spllt_b200_solve_phase": (None, [vp, C.c_int, vp, C.c_int, C.c_int]),
+        "spllt_b200_xw_ptr": (vp, [vp, C.c_int]),
         "spllt_b200_factor_phase": (None, [vp, vp, vp, C.c_int]),
     }
     for name, (res, args) in sig.items():

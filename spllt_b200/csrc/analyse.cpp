@@ -733,83 +733,109 @@ static void build_pipe_schedule(Analysis& A) {
     for (int i = 0; i < A.pnodes[s].np; ++i) A.strip_node[A.pnodes[s].strip0 + i] = s;
   for (int s = 0; s < nn; ++s)
     if (A.nodes[s].parent >= 0) A.pnodes[s].pflag = A.pnodes[A.nodes[s].parent].strip0;
-  std::vector<int> ord;
-  for (int s = 0; s < nn; ++s)
-    if (A.nodes[s].depth0 >= cut) ord.push_back(s);
-  std::stable_sort(ord.begin(), ord.end(),
-                   [&](int a, int b) { return A.nodes[a].depth0 < A.nodes[b].depth0; });
+  // Which nodes go into which pair of lists.  Single GPU: one pair holding every node at or
+  // above the cut.  Multi-GPU: list 0 = the subtrees this rank owns, list 1 = the
+  // shared upper tree (solved redundantly on every rank between two all-reduces of the work
+  // vector); each list has its own per-strip expected counts -- a contribution that crosses from
+  // a subtree into the upper tree is complete when the all-reduce is, so it is not counted.
+  const bool multi = A.world > 1;
   A.pexpect.assign(strip, 0);
-  auto dests = [&](int s, int r0, int r1, int* begin, int* count) {
-    // distinct ancestor STRIPS owning rows [r0, r1) of node s (index is sorted => runs).
-    // forward: the strips whose counters the task bumps; backward: the strips it waits for.
-    *begin = (int)A.pipe_dest.size();
-    const int* idx = A.index.data() + A.nodes[s].idx_off;
-    int last = -1;
-    for (int r = r0; r < r1; ++r) {
-      const int d = A.col2node[idx[r]];
-      const int st = A.pnodes[d].strip0 + (idx[r] - A.nodes[d].sa) / PS;
-      if (st != last) {
-        A.pipe_dest.push_back(st);
-        A.pexpect[st]++;
-        A.pnodes[d].expect_f++;
-        last = st;
-      }
-    }
-    *count = (int)A.pipe_dest.size() - *begin;
-  };
-  // rows per BELOW task of a narrow node: large chunks where a tree level has many nodes, small
-  // ones near the top where a few tall nodes must be spread over the whole device
-  std::vector<i64> below_rows(A.ndepth + 1, 0);
-  auto is_small0 = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
-  for (int s : ord)
-    if (!is_small0(A.nodes[s]) && A.pnodes[s].np <= PIPE_FAT_NP) below_rows[A.nodes[s].depth0] += A.nodes[s].m - A.nodes[s].n;
+  A.pexpect_top.assign(strip, 0);
+  A.ptasks_ft.clear();
+  A.ptasks_bt.clear();
   const i64 level_tasks = getenv("SPLLT_B200_PIPE_LEVEL_TASKS") ? atoi(getenv("SPLLT_B200_PIPE_LEVEL_TASKS")) : PIPE_LEVEL_TASKS;
   const i64 task_bytes = getenv("SPLLT_B200_PIPE_TASK_KB") ? 1024 * (i64)atoi(getenv("SPLLT_B200_PIPE_TASK_KB")) : PIPE_TASK_BYTES;
-  auto chunk_of = [&](int s) {
-    if (A.pnodes[s].np > PIPE_FAT_NP) return PS;
-    const i64 by_level = (below_rows[A.nodes[s].depth0] / std::max<i64>(level_tasks, 1) + PS - 1) / PS * PS;
-    const i64 by_bytes = (task_bytes / (8 * (i64)A.nodes[s].n) + PS - 1) / PS * PS;   // enough bytes per task
-    return (int)std::max<i64>(PS, std::min<i64>(PIPE_FAT_ROWS, std::max(by_level, by_bytes)));
-  };
   auto is_small = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
-  for (int s : ord) {
-    const HNode& nd = A.nodes[s];
-    if (is_small(nd)) {
-      PTask t{s, P_SMALL, 0, 0, 0, 0, {0, 0}};
-      dests(s, nd.n, nd.m, &t.dest_begin, &t.dest_count);
-      A.ptasks_f.push_back(t);
-      continue;
+  for (int list = 0; list < (multi ? 2 : 1); ++list) {
+    std::vector<PTask>& TF = list == 0 ? A.ptasks_f : A.ptasks_ft;
+    std::vector<PTask>& TB = list == 0 ? A.ptasks_b : A.ptasks_bt;
+    std::vector<int>& EX = list == 0 ? A.pexpect : A.pexpect_top;
+    std::vector<char> in_list(nn, 0);
+    std::vector<int> ord;
+    for (int s = 0; s < nn; ++s) {
+      const bool take = multi ? (list == 0 ? A.nodes[s].owner == A.rank : A.nodes[s].owner < 0) : A.nodes[s].depth0 >= cut;
+      if (take) {
+        ord.push_back(s);
+        in_list[s] = 1;
+      }
     }
-    for (int i = 0; i < A.pnodes[s].np; ++i) A.ptasks_f.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
-    // the first 64 rows are their own task: they feed the parent's first strip (forward) and are
-    // the last to become ready (backward), i.e. they sit on the critical path of a chain of nodes
-    const int chunk = chunk_of(s);
-    for (int r = nd.n; r < nd.m;) {
-      const int rows = std::min(r == nd.n ? PS : chunk, nd.m - r);
-      PTask t{s, P_BELOW, r, rows, 0, 0, {0, 0}};
-      dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
-      A.ptasks_f.push_back(t);
-      r += rows;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return A.nodes[a].depth0 < A.nodes[b].depth0; });
+    auto dests = [&](int s, int r0, int r1, int* begin, int* count) {
+      // distinct ancestor STRIPS owning rows [r0, r1) of node s (index is sorted => runs).
+      // forward: the strips whose counters the task bumps; backward: the strips it waits for.
+      *begin = (int)A.pipe_dest.size();
+      const int* idx = A.index.data() + A.nodes[s].idx_off;
+      int last = -1;
+      for (int r = r0; r < r1; ++r) {
+        const int d = A.col2node[idx[r]];
+        const int st = A.pnodes[d].strip0 + (idx[r] - A.nodes[d].sa) / PS;
+        if (st != last) {
+          A.pipe_dest.push_back(st);
+          if (in_list[d]) EX[st]++;
+          A.pnodes[d].expect_f++;
+          last = st;
+        }
+      }
+      *count = (int)A.pipe_dest.size() - *begin;
+    };
+    // rows per BELOW task of a narrow node: large chunks where a tree level has many nodes, small
+    // ones near the top where a few tall nodes must be spread over the whole device
+    std::vector<i64> below_rows(A.ndepth + 1, 0);
+    for (int s : ord)
+      if (!is_small(A.nodes[s]) && A.pnodes[s].np <= PIPE_FAT_NP) below_rows[A.nodes[s].depth0] += A.nodes[s].m - A.nodes[s].n;
+    auto chunk_of = [&](int s) {
+      if (A.pnodes[s].np > PIPE_FAT_NP) return PS;
+      const i64 by_level = (below_rows[A.nodes[s].depth0] / std::max<i64>(level_tasks, 1) + PS - 1) / PS * PS;
+      const i64 by_bytes = (task_bytes / (8 * (i64)A.nodes[s].n) + PS - 1) / PS * PS;   // enough bytes per task
+      return (int)std::max<i64>(PS, std::min<i64>(PIPE_FAT_ROWS, std::max(by_level, by_bytes)));
+    };
+    for (int s : ord) {
+      const HNode& nd = A.nodes[s];
+      if (is_small(nd)) {
+        PTask t{s, P_SMALL, 0, 0, 0, 0, {0, 0}};
+        dests(s, nd.n, nd.m, &t.dest_begin, &t.dest_count);
+        TF.push_back(t);
+        continue;
+      }
+      for (int i = 0; i < A.pnodes[s].np; ++i) TF.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
+      // the first 64 rows are their own task: they feed the parent's first strip (forward) and are
+      // the last to become ready (backward), i.e. they sit on the critical path of a chain of nodes
+      const int chunk = chunk_of(s);
+      for (int r = nd.n; r < nd.m;) {
+        const int rows = std::min(r == nd.n ? PS : chunk, nd.m - r);
+        PTask t{s, P_BELOW, r, rows, 0, 0, {0, 0}};
+        dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
+        TF.push_back(t);
+        r += rows;
+      }
+    }
+    // the backward tasks reuse the forward tasks' strip lists (same row ranges)
+    std::vector<std::vector<PTask>> of_node(nn);
+    for (const PTask& t : TF)
+      if (t.kind != P_DIAG) of_node[t.node].push_back(t);
+    for (auto it = ord.rbegin(); it != ord.rend(); ++it) {
+      const int s = *it;
+      const HNode& nd = A.nodes[s];
+      if (is_small(nd)) {
+        TB.push_back(of_node[s][0]);
+        continue;
+      }
+      // bottom chunk first: its rows belong to the highest ancestors, which finish first
+      for (auto t = of_node[s].rbegin(); t != of_node[s].rend(); ++t) {
+        TB.push_back(*t);
+        A.pnodes[s].expect_b++;
+      }
+      for (int i = A.pnodes[s].np - 1; i >= 0; --i) TB.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
     }
   }
-  // the backward tasks reuse the forward tasks' strip lists (same row ranges)
-  std::vector<std::vector<PTask>> of_node(nn);
-  for (const PTask& t : A.ptasks_f)
-    if (t.kind != P_DIAG) of_node[t.node].push_back(t);
-  for (auto it = ord.rbegin(); it != ord.rend(); ++it) {
-    const int s = *it;
-    const HNode& nd = A.nodes[s];
-    if (is_small(nd)) {
-      A.ptasks_b.push_back(of_node[s][0]);
-      continue;
+  // multi-GPU: pivot columns this rank keeps when the work vector is summed over the ranks
+  A.col_keep.assign(A.n, 1);
+  if (multi)
+    for (int s = 0; s < nn; ++s) {
+      const int own = A.nodes[s].owner;
+      const char keep = own == A.rank || (own < 0 && A.rank == 0);
+      for (int c = A.nodes[s].sa; c <= A.nodes[s].en; ++c) A.col_keep[c] = keep;
     }
-    // bottom chunk first: its rows belong to the highest ancestors, which finish first
-    for (auto t = of_node[s].rbegin(); t != of_node[s].rend(); ++t) {
-      A.ptasks_b.push_back(*t);
-      A.pnodes[s].expect_b++;
-    }
-    for (int i = A.pnodes[s].np - 1; i >= 0; --i) A.ptasks_b.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
-  }
 }
 
 void build_solve_schedule(Analysis& A) {
@@ -822,6 +848,7 @@ void build_solve_schedule(Analysis& A) {
     A.solve_cut = e ? atoi(e) : 0;
     const char* l = getenv("SPLLT_B200_SOLVE_LEVELSET");
     if (l && atoi(l)) A.solve_cut = 1 << 30;
+    if (A.world > 1) A.solve_cut = 0;   // the multi-GPU solve runs entirely in the persistent kernels
   }
   {
     const char* e = getenv("SPLLT_B200_PIPE_MAX_NRHS");

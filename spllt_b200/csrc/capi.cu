@@ -628,6 +628,15 @@ void spllt_b200_unpack_bcol(void* akeep, void* fkeep, int node, int c, const dou
   launch_unpack(e->arena + off, ld, rows, cols, d_buf, e->stream);
 }
 int spllt_b200_dist_top(void* akeep) { return AA(akeep)->dist_top; }
+void spllt_b200_solve_phase(void* fkeep, int nrhs, double* d_x, int ldx, int phase) {
+  EE(fkeep)->solve_phase(d_x, ldx, nrhs, phase);
+}
+void* spllt_b200_xw_ptr(void* fkeep, int nrhs) {
+  Engine* e = EE(fkeep);
+  e->upload_tables();
+  e->ensure_solve_buffers(nrhs);
+  return e->d_xw;
+}
 
 void spllt_b200_factor_phase(void* akeep, void* fkeep, const double* d_val, int phase) {
   (void)akeep;

@@ -140,6 +140,14 @@ void Engine::upload_tables() {
       for (const PTask& t : src) td.push_back(PTaskD{t, S.pnodes[t.node]});
       (dir == 0 ? d_ptask_f : d_ptask_b) = upload(td);
     }
+    for (int dir = 0; dir < 2; ++dir) {   // multi-GPU: upper-tree lists
+      const std::vector<PTask>& src = dir == 0 ? S.ptasks_ft : S.ptasks_bt;
+      td.clear();
+      for (const PTask& t : src) td.push_back(PTaskD{t, S.pnodes[t.node]});
+      (dir == 0 ? d_ptask_ft : d_ptask_bt) = upload(td);
+    }
+    d_pexpect_top = upload(S.pexpect_top);
+    d_col_keep = upload(S.col_keep);
   }
   d_pdest = upload(S.pipe_dest);
   d_strip_node = upload(S.strip_node);
@@ -406,6 +414,46 @@ void Engine::ensure_dinv() {
   dinv_valid = true;
 }
 
+// Multi-GPU solve, one call per phase; the caller all-reduces the work vector (xw_ptr) over the
+// ranks after phases 1 and 4.  0: permute the right-hand side in and drop the entries this rank
+// does not own; 1: forward sweep of the rank's subtrees; 2: forward sweep of the upper tree;
+// 3: backward sweep of the upper tree; 4: backward sweep of the rank's subtrees, then drop the
+// entries it does not own; 5: permute the solution out.
+void Engine::solve_phase(double* dx, int ldx, int nrhs, int phase) {
+  upload_tables();
+  if (A->n == 0 || nrhs <= 0) return;
+  ensure_solve_buffers(nrhs);
+  ensure_dinv();
+  const Analysis& S = *A;
+  cudaStream_t st = stream;
+  switch (phase) {
+    case 0:
+      launch_permute_in(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
+      launch_mask_rows(d_xw, d_col_keep, S.n, nrhs, st);
+      break;
+    case 1:
+      launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+                        S.nstrips, S.nnodes, d_psync, st);
+      break;
+    case 2:
+      launch_solve_pipe(true, d_ptask_ft, (int)S.ptasks_ft.size(), d_pdest, d_pexpect_top, arena, d_dinv, d_index, d_xw,
+                        nrhs, S.nstrips, S.nnodes, d_psync, st);
+      break;
+    case 3:
+      launch_solve_pipe(false, d_ptask_bt, (int)S.ptasks_bt.size(), d_pdest, d_pexpect_top, arena, d_dinv, d_index, d_xw,
+                        nrhs, S.nstrips, S.nnodes, d_psync + psync_ints, st);
+      break;
+    case 4:   // same flag region as phase 3: the subtrees wait on the flags of the upper tree
+      launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
+                        S.nstrips, S.nnodes, d_psync + psync_ints, st, nullptr, true);
+      launch_mask_rows(d_xw, d_col_keep, S.n, nrhs, st);
+      break;
+    case 5:
+      launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, st);
+      break;
+  }
+}
+
 void Engine::solve(double* dx, int ldx, int nrhs, int job) {
   upload_tables();
   if (A->n == 0 || nrhs <= 0) return;
@@ -614,6 +662,10 @@ void Engine::release() {
   cudaFree(d_pdest);
   cudaFree(d_strip_node);
   cudaFree(d_pexpect);
+  cudaFree(d_ptask_ft);
+  cudaFree(d_ptask_bt);
+  cudaFree(d_pexpect_top);
+  cudaFree(d_col_keep);
   cudaFree(d_dinv);
   if (d_psync) cudaFree(d_psync);
   d_psync = nullptr;

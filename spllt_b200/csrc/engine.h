@@ -59,6 +59,10 @@ struct Engine {
   int* d_pdest = nullptr;
   int* d_strip_node = nullptr;
   int* d_pexpect = nullptr;
+  PTaskD* d_ptask_ft = nullptr;   // multi-GPU: upper-tree lists
+  PTaskD* d_ptask_bt = nullptr;
+  int* d_pexpect_top = nullptr;
+  char* d_col_keep = nullptr;
   double* d_dinv = nullptr;       // [nstrips][64][64] inverses of the diagonal blocks
   bool dinv_valid = false;
   int* d_psync = nullptr;         // flags + counters: forward region, then backward region
@@ -89,6 +93,7 @@ struct Engine {
   void ensure_dinv();
   bool use_pipe(int nrhs) const;   // persistent pipelined kernels (few right-hand sides) or level-set launches
   void solve(double* dx, int ldx, int nrhs, int job);
+  void solve_phase(double* dx, int ldx, int nrhs, int phase);
   void profile_solve(double* dx, int ldx, int nrhs, double* ms6, const char* csv);
   void trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_f, unsigned long long* out_b);
   void solve_host(double* x, int nrhs, int job);

@@ -51,7 +51,9 @@ i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs);   // ints of flag / count
 // sync is zeroed (stream-ordered) before the kernel starts
 void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* dest, const int* expect,
                        const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
-                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace = nullptr);
+                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace = nullptr,
+                       bool keep_flags = false);
+void launch_mask_rows(double* xw, const char* keep, int n, int nrhs, cudaStream_t st);
 // inverses of the 64 x 64 diagonal blocks of every strip, dinv[strip][64][64] (once per factorization)
 void launch_invert_diag(const PNode* nodes, const int* strip_node, int nstrips, const double* arena, double* dinv,
                         cudaStream_t st);

@@ -214,6 +214,10 @@ struct Analysis {
   std::vector<int> pipe_dest;
   std::vector<int> strip_node;        // [nstrips] owning node
   std::vector<int> pexpect;           // [nstrips] forward: tasks that add into the strip's rows
+  // multi-GPU: ptasks_f / ptasks_b hold the subtrees this rank owns, these the shared upper tree
+  std::vector<PTask> ptasks_ft, ptasks_bt;
+  std::vector<int> pexpect_top;       // [nstrips] expected counts within the upper-tree lists
+  std::vector<char> col_keep;         // [n] pivot columns kept by this rank when the work vector is all-reduced
 };
 
 // analyse.cpp

@@ -699,50 +699,58 @@ __global__ void __launch_bounds__(PT, RC == 1 ? PIPE_OCC : 1) k_solve_pipe(const
 // is inverted by forward substitution, thread c computing column c of L_ii^-1.  Runs once per
 // factorization; the solves then replace the latency-bound substitution (a13 slv_solve: dtrsv /
 // dtrsm on the diagonal tile) by a 64 x 64 matrix-vector product.
+constexpr int ISL = PS + 2;   // even leading dimension: pairs of a row are 16-byte aligned
 __global__ void __launch_bounds__(PS) k_invert_diag(const PNode* __restrict__ nodes, const int* __restrict__ strip_node,
                                                     const double* __restrict__ arena, double* __restrict__ dinv) {
-  extern __shared__ __align__(16) double ism[];
-  double* Ls = ism;
-  double* Y = ism + PS * PSL;
-  double* rd = Y + PS * PSL;
+  __shared__ __align__(16) double Ls[PS * ISL];
   const int strip = blockIdx.x, c = threadIdx.x;
   const PNode nd = nodes[strip_node[strip]];
   const int i = strip - nd.strip0, r0 = i * PS, rw = min(PS, nd.n - r0);
   const double* D = arena + nd.off + (i64)r0 * nd.ld + r0;
   for (int idx = c; idx < PS * PS; idx += PS) {
     const int r = idx >> 6, cc = idx & (PS - 1);
-    Ls[r * PSL + cc] = (r < rw && cc <= r) ? D[(i64)r * nd.ld + cc] : 0.0;
+    Ls[r * ISL + cc] = (r < rw && cc <= r) ? D[(i64)r * nd.ld + cc] : 0.0;
   }
   __syncthreads();
-  {
-    const double d = c < rw ? Ls[c * PSL + c] : 0.0;
-    rd[c] = d != 0.0 ? 1.0 / d : 0.0;
+  {   // the diagonal is only ever divided by: keep its reciprocal (0 for rows beyond the strip)
+    const double d = Ls[c * ISL + c];
+    Ls[c * ISL + c] = d != 0.0 ? 1.0 / d : 0.0;
   }
   __syncthreads();
-  // column c of the inverse: y_r = (delta_rc - sum_{k<r} L[r][k] y_k) / L[r][r]; y_k = 0 for k < c
-  for (int r = 0; r < rw; ++r) {
-    double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = c & ~3;   // rows above c hold zeros; every thread only reads its own column of Y
-    for (; k + 3 < r; k += 4) {
-      s0 = fma(-Ls[r * PSL + k], Y[k * PSL + c], s0);
-      s1 = fma(-Ls[r * PSL + k + 1], Y[(k + 1) * PSL + c], s1);
-      s2 = fma(-Ls[r * PSL + k + 2], Y[(k + 2) * PSL + c], s2);
-      s3 = fma(-Ls[r * PSL + k + 3], Y[(k + 3) * PSL + c], s3);
+  // column c of the inverse stays in registers (the loops are fully unrolled, so y[] is indexed
+  // statically): y_r = (delta_rc - sum_{k<r} L[r][k] y_k) / L[r][r]; rows above c come out as 0
+  double y[PS];
+#pragma unroll
+  for (int r = 0; r < PS; ++r) {
+    double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < r; k += 2) {
+      const double2 l = *reinterpret_cast<const double2*>(Ls + r * ISL + k);
+      s0 = fma(-l.x, y[k], s0);
+      s1 = fma(-l.y, y[k + 1], s1);
     }
-    for (; k < r; ++k) s0 = fma(-Ls[r * PSL + k], Y[k * PSL + c], s0);
-    Y[r * PSL + c] = (r >= c) ? ((s0 + s1) + (s2 + s3)) * rd[r] : 0.0;
+    if (r & 1) s0 = fma(-Ls[r * ISL + r - 1], y[r - 1], s0);
+    y[r] = (s0 + s1) * Ls[r * ISL + r];
   }
-  for (int r = rw; r < PS; ++r) Y[r * PSL + c] = 0.0;
-  __syncthreads();
   double* out = dinv + (i64)strip * (PS * PS);
-  for (int idx = c; idx < PS * PS; idx += PS) out[idx] = Y[(idx >> 6) * PSL + (idx & (PS - 1))];
+#pragma unroll
+  for (int r = 0; r < PS; ++r) out[r * PS + c] = y[r];
 }
 
-constexpr int INVERT_SMEM = (2 * PS * PSL + PS) * (int)sizeof(double);
 void launch_invert_diag(const PNode* nodes, const int* strip_node, int nstrips, const double* arena, double* dinv,
                         cudaStream_t st) {
   if (nstrips <= 0) return;
-  k_invert_diag<<<nstrips, PS, INVERT_SMEM, st>>>(nodes, strip_node, arena, dinv);
+  k_invert_diag<<<nstrips, PS, 0, st>>>(nodes, strip_node, arena, dinv);
+}
+
+// multi-GPU: zero the entries of the work vector this rank does not own before it is summed
+__global__ void k_mask_rows(double* __restrict__ xw, const char* __restrict__ keep, i64 n, int nrhs) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * nrhs && !keep[i / nrhs]) xw[i] = 0.0;
+}
+void launch_mask_rows(double* xw, const char* keep, int n, int nrhs, cudaStream_t st) {
+  const i64 tot = (i64)n * nrhs;
+  if (tot > 0) k_mask_rows<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(xw, keep, n, nrhs);
 }
 
 static int pipe_smem(int rc) { return (rc == 1 ? Sm<1>::TOTAL : Sm<PIPE_RC>::TOTAL) * (int)sizeof(double); }
@@ -763,7 +771,6 @@ static int pipe_prepare() {
 }
 
 void pipe_init() {
-  CK(cudaFuncSetAttribute(k_invert_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, INVERT_SMEM));
   g_pipe_grid[0][1] = pipe_prepare<1, true>();
   g_pipe_grid[0][0] = pipe_prepare<1, false>();
   g_pipe_grid[1][1] = pipe_prepare<PIPE_RC, true>();
@@ -778,7 +785,7 @@ i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs) {
 
 void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* dest, const int* expect,
                        const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
-                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace) {
+                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace, bool keep_flags) {
   if (ntasks <= 0) return;
   const int mode = getenv("SPLLT_B200_PIPE_MODE") ? atoi(getenv("SPLLT_B200_PIPE_MODE")) : 0;
   PipeArgs a;
@@ -797,7 +804,9 @@ void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* des
   a.nstrips = nstrips;
   a.mode = mode;
   a.trace = trace;
-  CK(cudaMemsetAsync(sync, 0, pipe_sync_ints(nstrips, nnodes, nrhs) * sizeof(int), st));
+  // keep_flags: only the claim counter is reset -- the flags raised by the previous launch on the
+  // same region stay up (multi-GPU backward sweep: upper tree first, then this rank's subtrees)
+  CK(cudaMemsetAsync(sync, 0, (keep_flags ? 32 : pipe_sync_ints(nstrips, nnodes, nrhs)) * sizeof(int), st));
   const i64 total = (i64)ntasks * a.nchunk;
   const int rci = nrhs == 1 ? 0 : 1;
   const int grid = (int)std::min<i64>(total, g_pipe_grid[rci][fwd ? 1 : 0]);

@@ -10,6 +10,9 @@ factorized block-column-cyclically, owner computes: a rank factorizes the block 
 and computes every update whose DESTINATION block column it owns; each finished block column is
 broadcast once by its owner (NCCL) before anybody uses it as a source.  No reductions in the
 upper tree.  (SPLLT_B200_REPLICATED_TOP=1: every rank factorizes the whole upper tree instead.)
+
+Solve: see DistSpLLT.solve_dev -- subtree sweeps on their owners, the upper tree redundantly, two
+all-reduces of the work vector.
 """
 import ctypes as C
 
@@ -123,6 +126,32 @@ class DistSpLLT:
             self._dval = torch.empty(val.size, dtype=torch.float64, device="cuda")
         self._dval.copy_(torch.from_numpy(val), non_blocking=True)
         self.factor_dev(self._dval)
+
+    def solve_dev(self, d_x, nrhs=1):
+        """d_x: torch CUDA tensor, nrhs x n (row r = right-hand side r, i.e. column-major n x nrhs);
+        overwritten with the solution on EVERY rank.  Asynchronous on the stream.
+
+        world > 1: every rank sweeps the subtrees it owns in its own HBM, the upper
+        tree is swept redundantly by every rank (its factor is replicated), and the pivot-order work
+        vector (8 n nrhs bytes) is summed over the ranks twice: after the forward sweep of the
+        subtrees (contributions to the upper tree) and after the backward sweep (solution pieces)."""
+        s = self.local
+        if self.world == 1:
+            s.solve_dev(d_x.data_ptr(), nrhs)
+            return
+        import torch
+        import torch.distributed as dist
+        L = s.L
+        xw = torch.as_tensor(_DevArray(L.spllt_b200_xw_ptr(s.fkeep, nrhs), s.n * nrhs), device="cuda")
+        px = C.c_void_p(d_x.data_ptr())
+        L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 0)
+        L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 1)
+        dist.all_reduce(xw, op=dist.ReduceOp.SUM)
+        L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 2)
+        L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 3)
+        L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 4)
+        dist.all_reduce(xw, op=dist.ReduceOp.SUM)
+        L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 5)
 
     def wait(self):
         self.local.wait()

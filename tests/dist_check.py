@@ -129,8 +129,28 @@ def main():
     assert worst <= 1e-12, worst
     t = torch.tensor([worst], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # ---- distributed solve (subtree sweeps on their owners, upper tree redundantly, two all-reduces
+    # of the work vector) vs the single-GPU solve and the reference's backward-error gate
+    serr = 0.0
+    for nrhs in (1, 3):
+        xs = np.asfortranarray(np.tile(np.arange(1.0, nrhs + 1), (n, 1)) + 0.5 * np.cos(np.arange(n))[:, None])
+        b = np.asfortranarray(M.matvec(n, ptr, row, val, xs))
+        for rep in range(2):      # the second call replays with flags / counters reset
+            dx = torch.tensor(b.T.copy(), device="cuda")
+            d.solve_dev(dx, nrhs)
+            d.wait()
+            torch.cuda.synchronize()
+        x = np.asfortranarray(dx.cpu().numpy().T)
+        ok, err = sp.chkerr(n, ptr, row, val, x, b)
+        assert ok == nrhs and err.max() <= 1e-14, err
+        xr = b.copy(order="F")
+        ref.prepare_solve(nrhs)
+        ref.solve(xr, 0)
+        assert np.max(np.abs(x - xr)) <= 1e-10 * np.abs(xr).max()
+        serr = max(serr, float(err.max()))
     if rank == 0:
-        print("dist_check gpu ok: world %d, max rel diff vs single-GPU factor %.2e; %s" % (world, t.item(), d.describe()))
+        print("dist_check gpu ok: world %d, max rel diff vs single-GPU factor %.2e, distributed solve bwd err %.2e; %s"
+              % (world, t.item(), serr, d.describe()))
     dist.destroy_process_group()
 
 
