@@ -257,7 +257,7 @@ def main():
     # ---------------- solve: seconds per RHS, achieved HBM bandwidth (single-GPU path)
     solve = None
     parity = None
-    if world == 1:
+    if True:
         nrhs = args.nrhs
         from spllt_b200 import matrices as M
         xs = np.asfortranarray(np.tile(np.arange(1.0, nrhs + 1), (n, 1)))
@@ -265,15 +265,21 @@ def main():
         reps = max(args.steps, 3)
         d_rhs = [torch.tensor(rhs.T.copy(), device="cuda") for _ in range(reps + 2)]
         for d in d_rhs[:2]:
-            s.solve_dev(d.data_ptr(), nrhs)
+            solver.solve_dev(d, nrhs)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         a3, b3 = ev(), ev()
         a3.record()
         for d in d_rhs[2:]:
-            s.solve_dev(d.data_ptr(), nrhs)
+            solver.solve_dev(d, nrhs)
         b3.record()
         torch.cuda.synchronize()
         ms_solve = a3.elapsed_time(b3) / reps
+        if world > 1:
+            t = torch.tensor([ms_solve], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_solve = float(t.item())
         x = np.asfortranarray(d_rhs[2].cpu().numpy().T)
         ok, err = sp.chkerr(n, ptr, row, val, x, rhs)
         nfac = s.num_factor
@@ -283,13 +289,22 @@ def main():
         sbytes = 2 * (8 * nfac + 16 * n * nrhs + 24 * upd * nrhs)
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        if world > 1:
+            path = ("multi-GPU: persistent pipelined kernels on the rank's subtrees, upper tree redundantly, "
+                    "two NCCL all-reduces of the work vector")
+        elif nrhs <= 8 and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET"):
+            path = "persistent pipelined kernels k_solve_pipe<fwd>/<bwd> (64-row strips, flags in HBM)"
+        else:
+            path = "level-set launches k_fwd_diag/k_fwd_upd/k_bwd_upd/k_bwd_diag"
         solve = {"nrhs": nrhs, "seconds": ms_solve / 1e3, "seconds_per_rhs": ms_solve / 1e3 / nrhs,
                  "algorithmic_bytes": sbytes, "achieved_gbs": sbytes / ms_solve / 1e6, "hbm_peak_gbs": hbm_peak,
-                 "frac_of_hbm": sbytes / ms_solve / 1e6 / hbm_peak, "launches": int(L.spllt_b200_solve_launches(s.fkeep, 0)),
-                 "path": ("persistent pipelined kernels k_solve_pipe<fwd>/<bwd> (64-row strips, flags in HBM)"
-                          if nrhs <= 8 and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET") else
-                          "level-set launches k_fwd_diag/k_fwd_upd/k_bwd_upd/k_bwd_diag"),
-                 "profile_ms": s.profile_solve(d_rhs[0].data_ptr(), nrhs)}
+                 "frac_of_hbm": sbytes / ms_solve / 1e6 / hbm_peak / max(world, 1),
+                 "launches": int(L.spllt_b200_solve_launches(s.fkeep, 0)) if world == 1 else 8, "path": path}
+        if world == 1:
+            solve["profile_ms"] = s.profile_solve(d_rhs[0].data_ptr(), nrhs)
+            tpath = os.path.join(ROOT, "profiles", "solve_traffic.json")
+            if os.path.exists(tpath):   # dram bytes of k_solve_pipe<fwd> + <bwd> from one ncu --set full capture
+                solve["traffic"] = json.load(open(tpath))
         parity = {"scaled_backward_error_max": float(err.max()), "rhs_ok": int(ok), "nrhs": nrhs, "tol": 1e-14,
                   "forward_error_max": float(np.abs(x - xs).max() / np.abs(xs).max()), "pivot_flag": int(pivot)}
 

@@ -168,6 +168,9 @@ void Engine::ensure_solve_buffers(int nrhs) {
   CK(cudaMalloc(&d_xw, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
   CK(cudaMalloc(&d_x, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
   CK(cudaMemset(d_xw, 0, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
+  if (d_xm) CK(cudaFree(d_xm));
+  xm_doubles = std::max<i64>((i64)A->n * nrhs, 1);
+  CK(cudaMalloc(&d_xm, 2 * xm_doubles * sizeof(double)));   // mailboxes of the forward / backward sweep
   if (d_psync) CK(cudaFree(d_psync));
   psync_ints = pipe_sync_ints(A->nstrips, A->nnodes, nrhs);
   CK(cudaMalloc(&d_psync, 2 * psync_ints * sizeof(int)));
@@ -390,13 +393,13 @@ void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
       launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
     }
     if (pipe)
-      launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                        S.nstrips, S.nnodes, d_psync, st);
+      launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm, nrhs,
+                        S.nstrips, S.nnodes, S.n, d_psync, st);
   }
   if (job == 0 || job == 2) {
     if (pipe)
-      launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                        S.nstrips, S.nnodes, d_psync + psync_ints, st);
+      launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm + xm_doubles, nrhs,
+                        S.nstrips, S.nnodes, S.n, d_psync + psync_ints, st);
     for (int d = S.ndepth - 1; d >= 0; --d) {
       const SolveLaunch& L = SL[d];
       launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
@@ -432,20 +435,18 @@ void Engine::solve_phase(double* dx, int ldx, int nrhs, int phase) {
       launch_mask_rows(d_xw, d_col_keep, S.n, nrhs, st);
       break;
     case 1:
-      launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                        S.nstrips, S.nnodes, d_psync, st);
+      launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm, nrhs,
+                        S.nstrips, S.nnodes, S.n, d_psync, st);
       break;
     case 2:
-      launch_solve_pipe(true, d_ptask_ft, (int)S.ptasks_ft.size(), d_pdest, d_pexpect_top, arena, d_dinv, d_index, d_xw,
-                        nrhs, S.nstrips, S.nnodes, d_psync, st);
+      launch_solve_pipe(true, d_ptask_ft, (int)S.ptasks_ft.size(), d_pdest, d_pexpect_top, arena, d_dinv, d_index, d_xw, d_xm, nrhs, S.nstrips, S.nnodes, S.n, d_psync, st);
       break;
     case 3:
-      launch_solve_pipe(false, d_ptask_bt, (int)S.ptasks_bt.size(), d_pdest, d_pexpect_top, arena, d_dinv, d_index, d_xw,
-                        nrhs, S.nstrips, S.nnodes, d_psync + psync_ints, st);
+      launch_solve_pipe(false, d_ptask_bt, (int)S.ptasks_bt.size(), d_pdest, d_pexpect_top, arena, d_dinv, d_index, d_xw, d_xm + xm_doubles, nrhs, S.nstrips, S.nnodes, S.n, d_psync + psync_ints, st);
       break;
     case 4:   // same flag region as phase 3: the subtrees wait on the flags of the upper tree
-      launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                        S.nstrips, S.nnodes, d_psync + psync_ints, st, nullptr, true);
+      launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm + xm_doubles, nrhs,
+                        S.nstrips, S.nnodes, S.n, d_psync + psync_ints, st, nullptr, true);
       launch_mask_rows(d_xw, d_col_keep, S.n, nrhs, st);
       break;
     case 5:
@@ -522,12 +523,12 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
     recs.push_back({1, d, L.upd_count});
   }
   if (pipe) {
-  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
-                    S.nnodes, d_psync, st);
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm, nrhs, S.nstrips,
+                    S.nnodes, S.n, d_psync, st);
   mark();
   recs.push_back({4, -1, (long long)S.ptasks_f.size()});
-  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                    S.nstrips, S.nnodes, d_psync + psync_ints, st);
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm + xm_doubles, nrhs,
+                    S.nstrips, S.nnodes, S.n, d_psync + psync_ints, st);
   mark();
   recs.push_back({5, -1, (long long)S.ptasks_b.size()});
   }
@@ -576,10 +577,10 @@ void Engine::trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_
     launch_fwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, stream);
     launch_fwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
   }
-  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs, S.nstrips,
-                    S.nnodes, d_psync, stream, tf);
-  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, nrhs,
-                    S.nstrips, S.nnodes, d_psync + psync_ints, stream, tb);
+  launch_solve_pipe(true, d_ptask_f, (int)S.ptasks_f.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm, nrhs, S.nstrips,
+                    S.nnodes, S.n, d_psync, stream, tf);
+  launch_solve_pipe(false, d_ptask_b, (int)S.ptasks_b.size(), d_pdest, d_pexpect, arena, d_dinv, d_index, d_xw, d_xm + xm_doubles, nrhs,
+                    S.nstrips, S.nnodes, S.n, d_psync + psync_ints, stream, tb);
   for (int d = S.ndepth - 1; d >= 0; --d) {
     const SolveLaunch& L = S.slaunch[d];
     launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
@@ -669,6 +670,8 @@ void Engine::release() {
   cudaFree(d_dinv);
   if (d_psync) cudaFree(d_psync);
   d_psync = nullptr;
+  if (d_xm) cudaFree(d_xm);
+  d_xm = nullptr;
   cudaFree(d_index);
   cudaFree(d_porder);
   if (d_xw) cudaFree(d_xw);

@@ -67,6 +67,8 @@ struct Engine {
   bool dinv_valid = false;
   int* d_psync = nullptr;         // flags + counters: forward region, then backward region
   i64 psync_ints = 0;             // ints per region
+  double* d_xm = nullptr;         // mailbox copies of x (self-validating words): forward, then backward
+  i64 xm_doubles = 0;
   int* d_index = nullptr;
   int* d_porder = nullptr;
   double* d_xw = nullptr;  // pivot-order work vector, n x nrhs row-major (persists between job 1 and job 2)

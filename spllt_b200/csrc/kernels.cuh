@@ -50,8 +50,8 @@ int pipe_chunks(int nrhs);
 i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs);   // ints of flag / counter storage for one sweep
 // sync is zeroed (stream-ordered) before the kernel starts
 void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* dest, const int* expect,
-                       const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
-                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace = nullptr,
+                       const double* arena, const double* dinv, const int* index, double* xw, double* xm, int nrhs,
+                       int nstrips, int nnodes, int n, int* sync, cudaStream_t st, unsigned long long* trace = nullptr,
                        bool keep_flags = false);
 void launch_mask_rows(double* xw, const char* keep, int n, int nrhs, cudaStream_t st);
 // inverses of the 64 x 64 diagonal blocks of every strip, dinv[strip][64][64] (once per factorization)

@@ -86,6 +86,22 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Mailbox: a second copy of x (xm, pre-set to an all-ones NaN pattern by a memset) whose entries are
+// SELF-VALIDATING 8-byte words.  A strip writes its x there straight after the matrix-vector
+// product -- before the barrier, the fence and the flag that everybody else waits for -- and the
+// strips / rows below of the same node poll the values themselves: the critical chain of a node
+// saves a membar and a dependent load per 64 columns.
+__device__ __forceinline__ double ld_mailbox(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mailbox(double* p, double v) {
+  if (__double_as_longlong(v) == -1LL) v = __longlong_as_double(0x7ff8000000000000LL);   // never publish the "empty" pattern
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool mailbox_empty(double v) { return __double_as_longlong(v) == -1LL; }
+
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -96,8 +112,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 //   2: waiters back off (nanosleep) in proportion to their distance from the critical path
 //   4: poll with ld.relaxed (no L1 invalidation per poll); x is read with L2-coherent loads behind
 //      the control dependency   8: ... plus one fence.acq_rel after a successful poll
-//  16: no L2 prefetch of a task's rows at task start
-enum { M_FENCE_ACQREL = 1, M_BACKOFF = 2, M_POLL_RELAXED = 4, M_POLL_FENCE = 8, M_NO_PREFETCH = 16 };
+//  16: no L2 prefetch of a task's rows at task start   32: strips wait on flags, not on the mailbox
+enum { M_FENCE_ACQREL = 1, M_BACKOFF = 2, M_POLL_RELAXED = 4, M_POLL_FENCE = 8, M_NO_PREFETCH = 16, M_NO_MAILBOX = 32, M_NO_MAILBOX_BWD = 64 };
 __device__ __forceinline__ void fence_gpu(int mode) {
   if (mode & M_FENCE_ACQREL)
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -162,6 +178,7 @@ struct PipeArgs {
   const double* dinv;
   const int* index;
   double* xw;
+  double* xm;       // mailbox copy of x (see ld_mailbox), n x nrhs, all-ones pattern = not yet published
   int* sync;        // [0] claim counter; per chunk c: flags at 32 + c*stride, node counters after the flags
   int ntasks, nrhs, nchunk, stride, nstrips;
   int mode;                    // experiment switches, see M_*
@@ -231,7 +248,10 @@ __device__ __forceinline__ void strip_matvec(int rw, double* xg, const PipeArgs&
     for (int q = 0; q < RC; ++q) {
       const double x = (s[0][q] + s[1][q]) + (s[2][q] + s[3][q]);
       (pipe_sm + Sm<RC>::XS)[r * RC + q] = x;
-      if (r < rw && q < c.nr) __stcg(xg + (i64)r * a.nrhs + q, x);
+      if (r < rw && q < c.nr) {
+        st_mailbox(a.xm + (xg - a.xw) + (i64)r * a.nrhs + q, x);
+        __stcg(xg + (i64)r * a.nrhs + q, x);
+      }
     }
   }
 }
@@ -287,16 +307,31 @@ __device__ __forceinline__ void fwd_strip(const PNode& nd, int node, int i, bool
               b[q] = (lane < RPW && row < rw && q < c.nr) ? __ldcg(xg + (i64)row * a.nrhs + q) : 0.0;
           }
         }
-        ready = j + wait_run(c.flags + nd.strip0 + j, 1, i - j, lane, a.mode, i - j);
+        if (a.mode & M_NO_MAILBOX) ready = j + wait_run(c.flags + nd.strip0 + j, 1, i - j, lane, a.mode, i - j);
+      }
+      double x0[RC], x1[RC];
+      if (a.mode & M_NO_MAILBOX) {
+        const double* xp = a.xw + (i64)(nd.sa + j * PS + 2 * lane) * a.nrhs + c.rc0;
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          x0[q] = q < c.nr ? __ldcg(xp + q) : 0.0;
+          x1[q] = q < c.nr ? __ldcg(xp + a.nrhs + q) : 0.0;
+        }
+      } else {
+        const double* xp = a.xm + (i64)(nd.sa + j * PS + 2 * lane) * a.nrhs + c.rc0;
+        for (;;) {   // poll the values themselves
+          bool empty = false;
+#pragma unroll
+          for (int q = 0; q < RC; ++q) {
+            x0[q] = q < c.nr ? ld_mailbox(xp + q) : 0.0;
+            x1[q] = q < c.nr ? ld_mailbox(xp + a.nrhs + q) : 0.0;
+            empty |= mailbox_empty(x0[q]) | mailbox_empty(x1[q]);
+          }
+          if (!__any_sync(FULL, empty)) break;
+        }
+        ready = j + 1;
       }
       if (c.tr && tid == 0 && j == i - 1) c.tr[4] = gtime();
-      const double* xp = a.xw + (i64)(nd.sa + j * PS + 2 * lane) * a.nrhs + c.rc0;
-      double x0[RC], x1[RC];
-#pragma unroll
-      for (int q = 0; q < RC; ++q) {
-        x0[q] = q < c.nr ? __ldcg(xp + q) : 0.0;
-        x1[q] = q < c.nr ? __ldcg(xp + a.nrhs + q) : 0.0;
-      }
 #pragma unroll
       for (int u = 0; u < RPW; ++u)
 #pragma unroll
@@ -367,14 +402,28 @@ __device__ __forceinline__ void fwd_below(const PNode& nd, int r0, int nrows, co
 #pragma unroll
     for (int u = 0; u < RPW; ++u)
       t[u] = (u < rv && colok) ? ld_stream2(Lr + (i64)u * ld + j * PS) : make_double2(0.0, 0.0);
-    if (j >= ready) ready = j + wait_run(c.flags + nd.strip0 + j, 1, np - j, lane, a.mode, np - j);
     const int col = j * PS + 2 * lane;
-    const double* xp = a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0;
     double x0[RC], x1[RC];
+    if (a.mode & M_NO_MAILBOX) {
+      if (j >= ready) ready = j + wait_run(c.flags + nd.strip0 + j, 1, np - j, lane, a.mode, np - j);
+      const double* xp = a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0;
 #pragma unroll
-    for (int q = 0; q < RC; ++q) {
-      x0[q] = (q < c.nr && col < nd.n) ? __ldcg(xp + q) : 0.0;
-      x1[q] = (q < c.nr && col + 1 < nd.n) ? __ldcg(xp + a.nrhs + q) : 0.0;
+      for (int q = 0; q < RC; ++q) {
+        x0[q] = (q < c.nr && col < nd.n) ? __ldcg(xp + q) : 0.0;
+        x1[q] = (q < c.nr && col + 1 < nd.n) ? __ldcg(xp + a.nrhs + q) : 0.0;
+      }
+    } else {
+      const double* xp = a.xm + (i64)(nd.sa + col) * a.nrhs + c.rc0;
+      for (;;) {
+        bool empty = false;
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          x0[q] = (q < c.nr && col < nd.n) ? ld_mailbox(xp + q) : 0.0;
+          x1[q] = (q < c.nr && col + 1 < nd.n) ? ld_mailbox(xp + a.nrhs + q) : 0.0;
+          empty |= mailbox_empty(x0[q]) | mailbox_empty(x1[q]);
+        }
+        if (!__any_sync(FULL, empty)) break;
+      }
     }
 #pragma unroll
     for (int u = 0; u < RPW; ++u)
@@ -524,20 +573,41 @@ __device__ __forceinline__ void bwd_strip(const PNode& nd, int node, int i, bool
 #pragma unroll
       for (int u = 0; u < RPW; ++u)
         t[u] = (rb + u < nd.n) ? ld_stream2(Lc + (i64)(j * PS + u) * ld) : make_double2(0.0, 0.0);
-      if (jj >= ready) ready = jj + wait_run(c.flags + nd.strip0 + j, -1, nj - jj, lane, a.mode, nj - jj);
-      if (jj == 0 && bvalid) bpre = __ldcg(xg + (i64)brow * a.nrhs + bq);
-      if (c.tr && tid == 0 && jj == nj - 1) c.tr[4] = gtime();
-      const double* xp = a.xw + (i64)(nd.sa + rb) * a.nrhs + c.rc0;
+      double xv[RPW][RC];
+      if (a.mode & M_NO_MAILBOX_BWD) {
+        if (jj >= ready) ready = jj + wait_run(c.flags + nd.strip0 + j, -1, nj - jj, lane, a.mode, nj - jj);
+        const double* xp = a.xw + (i64)(nd.sa + rb) * a.nrhs + c.rc0;
 #pragma unroll
-      for (int u = 0; u < RPW; ++u) {
-        const bool ok = rb + u < nd.n;
+        for (int u = 0; u < RPW; ++u)
 #pragma unroll
-        for (int q = 0; q < RC; ++q) {
-          const double xv = (ok && q < c.nr) ? __ldcg(xp + (i64)u * a.nrhs + q) : 0.0;
-          a0[q] = fma(t[u].x, xv, a0[q]);
-          a1[q] = fma(t[u].y, xv, a1[q]);
+          for (int q = 0; q < RC; ++q) xv[u][q] = (rb + u < nd.n && q < c.nr) ? __ldcg(xp + (i64)u * a.nrhs + q) : 0.0;
+      } else {
+        const double* xp = a.xm + (i64)(nd.sa + rb) * a.nrhs + c.rc0;
+        for (;;) {   // the 8 x values of this warp's rows (same addresses in every lane): poll the values
+          bool empty = false;
+#pragma unroll
+          for (int u = 0; u < RPW; ++u)
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+              xv[u][q] = (rb + u < nd.n && q < c.nr) ? ld_mailbox(xp + (i64)u * a.nrhs + q) : 0.0;
+              empty |= mailbox_empty(xv[u][q]);
+            }
+          // a warp whose 8 rows lie beyond the (partial) last strip has nothing to poll, but it must
+          // not run ahead: its threads read the strip's right-hand side next, which is final only
+          // once the node's last strip has started publishing
+          if (jj == 0) empty |= mailbox_empty(ld_mailbox(a.xm + (i64)(nd.sa + j * PS) * a.nrhs + c.rc0));
+          if (!__any_sync(FULL, empty)) break;
         }
       }
+      if (jj == 0 && bvalid) bpre = __ldcg(xg + (i64)brow * a.nrhs + bq);
+      if (c.tr && tid == 0 && jj == nj - 1) c.tr[4] = gtime();
+#pragma unroll
+      for (int u = 0; u < RPW; ++u)
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+          a0[q] = fma(t[u].x, xv[u][q], a0[q]);
+          a1[q] = fma(t[u].y, xv[u][q], a1[q]);
+        }
     }
   }
   if (c.tr && tid == 0) c.tr[5] = gtime() + (long long)(a0[0] == 12345.678);
@@ -784,8 +854,9 @@ i64 pipe_sync_ints(int nstrips, int nnodes, int nrhs) {
 }
 
 void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* dest, const int* expect,
-                       const double* arena, const double* dinv, const int* index, double* xw, int nrhs, int nstrips,
-                       int nnodes, int* sync, cudaStream_t st, unsigned long long* trace, bool keep_flags) {
+                       const double* arena, const double* dinv, const int* index, double* xw, double* xm, int nrhs,
+                       int nstrips, int nnodes, int n, int* sync, cudaStream_t st, unsigned long long* trace,
+                       bool keep_flags) {
   if (ntasks <= 0) return;
   const int mode = getenv("SPLLT_B200_PIPE_MODE") ? atoi(getenv("SPLLT_B200_PIPE_MODE")) : 0;
   PipeArgs a;
@@ -796,6 +867,7 @@ void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* des
   a.dinv = dinv;
   a.index = index;
   a.xw = xw;
+  a.xm = xm;
   a.sync = sync;
   a.ntasks = ntasks;
   a.nrhs = nrhs;
@@ -807,6 +879,7 @@ void launch_solve_pipe(bool fwd, const PTaskD* tasks, int ntasks, const int* des
   // keep_flags: only the claim counter is reset -- the flags raised by the previous launch on the
   // same region stay up (multi-GPU backward sweep: upper tree first, then this rank's subtrees)
   CK(cudaMemsetAsync(sync, 0, (keep_flags ? 32 : pipe_sync_ints(nstrips, nnodes, nrhs)) * sizeof(int), st));
+  if (!keep_flags) CK(cudaMemsetAsync(xm, 0xff, (size_t)n * nrhs * sizeof(double), st));   // mailbox: nothing published
   const i64 total = (i64)ntasks * a.nchunk;
   const int rci = nrhs == 1 ? 0 : 1;
   const int grid = (int)std::min<i64>(total, g_pipe_grid[rci][fwd ? 1 : 0]);
