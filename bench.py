@@ -292,7 +292,7 @@ def main():
         if world > 1:
             path = ("multi-GPU: persistent pipelined kernels on the rank's subtrees, upper tree redundantly, "
                     "two NCCL all-reduces of the work vector")
-        elif nrhs <= 8 and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET"):
+        elif nrhs <= L.spllt_b200_pipe_max_nrhs(s.akeep) and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET"):
             path = "persistent pipelined kernels k_solve_pipe<fwd>/<bwd> (64-row strips, flags in HBM)"
         else:
             path = "level-set launches k_fwd_diag/k_fwd_upd/k_bwd_upd/k_bwd_diag"

@@ -91,6 +91,10 @@ void spllt_b200_profile_solve(void *fkeep, int nrhs, double *d_x, int ldx, doubl
  * pflag}; dest: global strip ids (forward: counters the task bumps, backward: flags it waits for);
  * expect: per strip, how many forward tasks add into its rows */
 void spllt_b200_pipe_sizes(void *akeep, long long *out4);
+/* path selection of the solve: share of L's entries in nodes wider than 256 columns, and the largest
+ * nrhs served by the persistent kernels (0: level-set launches for every nrhs) */
+double spllt_b200_wide_frac(void *akeep);
+int spllt_b200_pipe_max_nrhs(void *akeep);
 /* diagnostic: one un-graphed solve with 8 globaltimer stamps (ns) per claimed task of the persistent
  * kernels {start, waits satisfied, solved, end, 4 strip-internal}; out_f / out_b hold 8 * tasks * ceil(nrhs / rc) values
  * (rc = 1 for nrhs == 1, else 4), in claim order */

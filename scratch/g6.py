@@ -51,6 +51,6 @@ E3 = ({}, {"SPLLT_B200_SOLVE_LEVELSET": "1"})
 if '2d' in which: run('p2d-200', M.poisson2d(200), 256, (1,), envs=E3)
 if '48' in which: run('p3d-48', M.poisson3d(48), 256, (1, 16), envs=E3)
 if '64' in which: run('p3d-64', M.poisson3d(64), 512, (1, 4, 16, 64), envs=({}, {"SPLLT_B200_SOLVE_LEVELSET": "1"}))
-if '80' in which: run('p3d-80', M.poisson3d(80), 512, (1, 16))
-if '100' in which: run('p3d-100', M.poisson3d(100), 768, (1, 16), envs=E3)
-if 'el' in which: run('el3d-60', M.elasticity3d(60), 768, (1,))
+if '80' in which: run('p3d-80', M.poisson3d(80), 512, (1, 16, 64), reps=5)
+if '100' in which: run('p3d-100', M.poisson3d(100), 768, (1, 16), reps=5)
+if 'el' in which: run('el3d-60', M.elasticity3d(60), 768, (1,), reps=5, envs=E3)

@@ -108,6 +108,8 @@ def load_library(path=None):
         "spllt_b200_node_owner": (C.c_int, [vp, C.c_int]),
         "spllt_b200_profile_solve": (None, [vp, C.c_int, vp, C.c_int, dp, C.c_char_p]),
         "spllt_b200_pipe_sizes": (None, [vp, C.POINTER(C.c_longlong)]),
+        "spllt_b200_wide_frac": (C.c_double, [vp]),
+        "spllt_b200_pipe_max_nrhs": (C.c_int, [vp]),
         "spllt_b200_trace_solve": (None, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_ulonglong),
                                           C.POINTER(C.c_ulonglong)]),
         "spllt_b200_get_pipe": (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

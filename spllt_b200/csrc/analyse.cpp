@@ -800,9 +800,17 @@ static void build_pipe_schedule(Analysis& A) {
       for (int i = 0; i < A.pnodes[s].np; ++i) TF.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
       // the first 64 rows are their own task: they feed the parent's first strip (forward) and are
       // the last to become ready (backward), i.e. they sit on the critical path of a chain of nodes
+      // ... and so do all rows that map to the parent (backward: none of them can start before the
+      // parent is complete), so those are cut into 64-row tasks that run side by side
       const int chunk = chunk_of(s);
+      int crit_end = nd.n + PS;
+      if (nd.parent >= 0) {
+        const int* idx = A.index.data() + nd.idx_off;
+        const int pend = A.nodes[nd.parent].en;
+        while (crit_end < nd.m && idx[crit_end] <= pend) ++crit_end;
+      }
       for (int r = nd.n; r < nd.m;) {
-        const int rows = std::min(r == nd.n ? PS : chunk, nd.m - r);
+        const int rows = std::min(r < crit_end ? PS : chunk, nd.m - r);
         PTask t{s, P_BELOW, r, rows, 0, 0, {0, 0}};
         dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
         TF.push_back(t);
@@ -851,8 +859,20 @@ void build_solve_schedule(Analysis& A) {
     if (A.world > 1) A.solve_cut = 0;   // the multi-GPU solve runs entirely in the persistent kernels
   }
   {
+    // Which path serves how many right-hand sides.  The persistent kernels win where the sweep is
+    // bound by the dependency chain of the assembly tree (few right-hand sides, most of L in
+    // narrow nodes); the level-set update kernels stream the rows below WIDE nodes better (more
+    // resident warps), so matrices whose factor sits mostly in wide nodes (large 3D fronts, e.g.
+    // the elasticity configuration) keep the level-set launches.  SPLLT_B200_PIPE_MAX_NRHS overrides.
+    double wide = 0, total = 0;
+    for (int s = 0; s < nn; ++s) {
+      const double e = (double)A.nodes[s].m * A.nodes[s].n;
+      total += e;
+      if (A.nodes[s].n > PIPE_FAT_NP * PS) wide += e;
+    }
+    A.wide_frac = total > 0 ? wide / total : 0;
     const char* e = getenv("SPLLT_B200_PIPE_MAX_NRHS");
-    A.pipe_max_nrhs = e ? atoi(e) : 8;
+    A.pipe_max_nrhs = e ? atoi(e) : (A.wide_frac > PIPE_WIDE_FRAC_MAX ? 0 : 8);
   }
   A.sbcols.clear();
   A.supds.clear();

@@ -524,6 +524,8 @@ void spllt_b200_trace_solve(void* fkeep, int nrhs, double* d_x, int ldx, unsigne
                             unsigned long long* out_b) {
   EE(fkeep)->trace_solve(d_x, ldx, nrhs, out_f, out_b);
 }
+double spllt_b200_wide_frac(void* akeep) { return AA(akeep)->wide_frac; }
+int spllt_b200_pipe_max_nrhs(void* akeep) { return AA(akeep)->pipe_max_nrhs; }
 void spllt_b200_pipe_sizes(void* akeep, long long* out4) {
   const Analysis& A = *AA(akeep);
   out4[0] = (long long)A.ptasks_f.size();

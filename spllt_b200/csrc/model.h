@@ -124,6 +124,7 @@ constexpr int PIPE_SMALL_ROWS = 256;  // nodes with n <= PS and m - n <= this ar
 constexpr int PIPE_FAT_NP = 4;        // nodes with at most this many strips: rows below them are streamed in
 constexpr int PIPE_FAT_ROWS = 512;    //   chunks of up to this many rows after the whole node is solved
 constexpr int PIPE_LEVEL_TASKS = 512; // ... sized so that a tree level yields about this many chunks
+constexpr double PIPE_WIDE_FRAC_MAX = 0.6;   // above this share of L in wide nodes the level-set path is kept
 constexpr int PIPE_TASK_BYTES = 64 * 1024;  // ... and a chunk streams at least this many bytes of L
 enum PipeKind { P_DIAG = 0, P_BELOW = 1, P_SMALL = 2 };
 struct PNode {
@@ -205,6 +206,7 @@ struct Analysis {
   std::vector<SolveLaunch> slaunch;   // one per depth: nodes below solve_cut (none by default)
   std::vector<SolveLaunch> slaunch_full;  // one per depth: ALL nodes (used when nrhs > pipe_max_nrhs)
   int pipe_max_nrhs = 8;              // more right-hand sides than this: level-set launches (RC = 8 kernels)
+  double wide_frac = 0;               // share of L's entries in nodes wider than PIPE_FAT_NP strips
   // pipelined solve: nodes with depth0 >= solve_cut run in the persistent kernels, the rest
   // (none by default) in the level-set launches above
   int solve_cut = 0;

@@ -666,6 +666,10 @@ __device__ __forceinline__ void bwd_below(const PNode& nd, int r0, int nrows, co
       const int ra = g * rpi, rb = min(cnt, ra + rpi);
       const int col = k * PS + 2 * lane;
       const bool colok = col < nd.ld;
+      // the whole item (<= 64 rows x 64 columns) -> L2 first; the register loads below then pay the
+      // HBM latency once per item instead of once per 8 rows
+      for (int rbase = ra; rbase < rb; rbase += RPW)
+        prefetch_tile(Lr - 2 * lane + (i64)(p * PS + rbase) * ld + k * PS, ld, rb - rbase, nd.ld - k * PS, lane);
       for (int rbase = ra; rbase < rb; rbase += RPW) {
         double2 t[RPW];
 #pragma unroll

@@ -318,16 +318,19 @@ def test_schedule_variants(case, env, monkeypatch):
 
 @pytest.mark.parametrize("env", [
     {},
+    {"SPLLT_B200_PIPE_MAX_NRHS": "8"},
     {"SPLLT_B200_SOLVE_LEVELSET": "1"},
-    {"SPLLT_B200_SOLVE_CUT": "2"},
-    {"SPLLT_B200_SOLVE_CUT": "5", "SPLLT_B200_GRAPH": "0"},
-], ids=["pipelined", "levelset", "cut2", "cut5-nograph"])
+    {"SPLLT_B200_SOLVE_CUT": "2", "SPLLT_B200_PIPE_MAX_NRHS": "8"},
+    {"SPLLT_B200_SOLVE_CUT": "5", "SPLLT_B200_GRAPH": "0", "SPLLT_B200_PIPE_MAX_NRHS": "8"},
+    {"SPLLT_B200_PIPE_MAX_NRHS": "8", "SPLLT_B200_PIPE_MODE": "96"},
+], ids=["auto", "pipelined", "levelset", "cut2", "cut5-nograph", "pipelined-flags-only"])
 @pytest.mark.parametrize("case", [SMALL[7], SMALL[11], MEDIUM[1], MEDIUM[2], MEDIUM[3]],
                          ids=ids([SMALL[7], SMALL[11], MEDIUM[1], MEDIUM[2], MEDIUM[3]]))
 @pytest.mark.parametrize("nrhs", [1, 6])
 def test_solve_variants(case, env, nrhs, monkeypatch):
-    """The persistent pipelined solve (default), the level-set launches, and hybrids of the two
-    give the oracle's solution; forward-only + backward-only equals the full solve."""
+    """The path chosen from the matrix structure, the persistent pipelined solve forced, the
+    level-set launches, hybrids of the two and the pipelined solve without the mailbox all give
+    the oracle's solution; forward-only + backward-only equals the full solve."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     s, o, mat = both(case)

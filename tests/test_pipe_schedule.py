@@ -186,3 +186,15 @@ def test_lists_replayed_numerically(case):
     x = np.asfortranarray(x)
     ok, err = chkerr(n, ptr, row, val, x, b)
     assert ok == nrhs and err.max() <= 1e-14, err
+
+
+def test_path_selection_follows_the_structure():
+    """Few right-hand sides go to the persistent kernels unless most of L sits in wide nodes."""
+    narrow = sp.SpLLT(nb=128)
+    n, ptr, row, val = M.poisson3d(24)
+    narrow.analyse(n, ptr, row)
+    assert narrow.L.spllt_b200_wide_frac(narrow.akeep) < 0.6 and narrow.L.spllt_b200_pipe_max_nrhs(narrow.akeep) == 8
+    wide = sp.SpLLT(nb=64)
+    n, ptr, row, val = M.random_spd(300, 0.3, 2)      # fills in completely: one dense node holds almost all of L
+    wide.analyse(n, ptr, row)
+    assert wide.L.spllt_b200_wide_frac(wide.akeep) > 0.6 and wide.L.spllt_b200_pipe_max_nrhs(wide.akeep) == 0
