@@ -195,6 +195,6 @@ def test_path_selection_follows_the_structure():
     narrow.analyse(n, ptr, row)
     assert narrow.L.spllt_b200_wide_frac(narrow.akeep) < 0.6 and narrow.L.spllt_b200_pipe_max_nrhs(narrow.akeep) == 8
     wide = sp.SpLLT(nb=64)
-    n, ptr, row, val = M.random_spd(300, 0.3, 2)      # fills in completely: one dense node holds almost all of L
+    n, ptr, row, val = M.random_spd(700, 0.2, 3)      # fills in completely: one dense node holds almost all of L
     wide.analyse(n, ptr, row)
     assert wide.L.spllt_b200_wide_frac(wide.akeep) > 0.6 and wide.L.spllt_b200_pipe_max_nrhs(wide.akeep) == 0
