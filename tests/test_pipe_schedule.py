@@ -195,6 +195,8 @@ def test_path_selection_follows_the_structure():
     narrow.analyse(n, ptr, row)
     assert narrow.L.spllt_b200_wide_frac(narrow.akeep) < 0.6 and narrow.L.spllt_b200_pipe_max_nrhs(narrow.akeep) == 8
     wide = sp.SpLLT(nb=64)
-    n, ptr, row, val = M.random_spd(700, 0.2, 3)      # fills in completely: one dense node holds almost all of L
+    n = 400                                            # a dense matrix: one supernode, 7 strips wide
+    ptr = np.concatenate([[1], 1 + np.cumsum(np.arange(n, 0, -1))]).astype(np.int32)
+    row = np.concatenate([np.arange(j + 1, n + 1) for j in range(n)]).astype(np.int32)
     wide.analyse(n, ptr, row)
     assert wide.L.spllt_b200_wide_frac(wide.akeep) > 0.6 and wide.L.spllt_b200_pipe_max_nrhs(wide.akeep) == 0
