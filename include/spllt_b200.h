@@ -91,6 +91,10 @@ void spllt_b200_profile_solve(void *fkeep, int nrhs, double *d_x, int ldx, doubl
  * pflag}; dest: global strip ids (forward: counters the task bumps, backward: flags it waits for);
  * expect: per strip, how many forward tasks add into its rows */
 void spllt_b200_pipe_sizes(void *akeep, long long *out4);
+/* multi-GPU (after spllt_b200_partition[_host]): spllt_b200_get_pipe returns the lists of the subtrees
+ * this rank owns, these return the lists of the shared upper tree (same record layout) */
+void spllt_b200_pipe_top_sizes(void *akeep, long long *sizes2);
+void spllt_b200_get_pipe_top(void *akeep, int *tasks_f, int *tasks_b, int *expect);
 /* path selection of the solve: share of L's entries in nodes wider than 256 columns, and the largest
  * nrhs served by the persistent kernels (0: level-set launches for every nrhs) */
 double spllt_b200_wide_frac(void *akeep);

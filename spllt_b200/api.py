@@ -108,6 +108,8 @@ def load_library(path=None):
         "spllt_b200_node_owner": (C.c_int, [vp, C.c_int]),
         "spllt_b200_profile_solve": (None, [vp, C.c_int, vp, C.c_int, dp, C.c_char_p]),
         "spllt_b200_pipe_sizes": (None, [vp, C.POINTER(C.c_longlong)]),
+        "spllt_b200_pipe_top_sizes": (None, [vp, C.POINTER(C.c_longlong)]),
+        "spllt_b200_get_pipe_top": (None, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "spllt_b200_wide_frac": (C.c_double, [vp]),
         "spllt_b200_pipe_max_nrhs": (C.c_int, [vp]),
         "spllt_b200_trace_solve": (None, [vp, C.c_int, vp, C.c_int, C.POINTER(C.c_ulonglong),
@@ -285,6 +287,19 @@ class SpLLT:
         up = lambda a: a.ctypes.data_as(C.POINTER(C.c_ulonglong))
         self.L.spllt_b200_trace_solve(self.fkeep, nrhs, C.c_void_p(d_x_ptr), self.n, up(f), up(b))
         return f, b
+
+    def pipe_top_tables(self):
+        """Multi-GPU: work lists of the shared upper tree: (tasks_f [k,6], tasks_b [k,6], expect [nstrips])."""
+        sz = np.zeros(4, np.int64)
+        self.L.spllt_b200_pipe_sizes(self.akeep, sz.ctypes.data_as(C.POINTER(C.c_longlong)))
+        s2 = np.zeros(2, np.int64)
+        self.L.spllt_b200_pipe_top_sizes(self.akeep, s2.ctypes.data_as(C.POINTER(C.c_longlong)))
+        tf = np.zeros((int(s2[0]), 6), np.int32)
+        tb = np.zeros((int(s2[1]), 6), np.int32)
+        ex = np.zeros(max(int(sz[2]), 1), np.int32)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        self.L.spllt_b200_get_pipe_top(self.akeep, ip(tf), ip(tb), ip(ex))
+        return tf, tb, ex[:int(sz[2])]
 
     def pipe_tables(self):
         """Work lists of the pipelined solve:

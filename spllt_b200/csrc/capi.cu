@@ -524,6 +524,23 @@ void spllt_b200_trace_solve(void* fkeep, int nrhs, double* d_x, int ldx, unsigne
                             unsigned long long* out_b) {
   EE(fkeep)->trace_solve(d_x, ldx, nrhs, out_f, out_b);
 }
+// multi-GPU: the upper-tree lists (sizes2 = {forward tasks, backward tasks}); same record layout
+void spllt_b200_pipe_top_sizes(void* akeep, long long* sizes2) {
+  const Analysis& A = *AA(akeep);
+  sizes2[0] = (long long)A.ptasks_ft.size();
+  sizes2[1] = (long long)A.ptasks_bt.size();
+}
+void spllt_b200_get_pipe_top(void* akeep, int* tasks_f, int* tasks_b, int* expect) {
+  const Analysis& A = *AA(akeep);
+  auto put = [](const std::vector<PTask>& v, int* o) {
+    for (const PTask& t : v) {
+      *o++ = t.node; *o++ = t.kind; *o++ = t.r0; *o++ = t.nrows; *o++ = t.dest_begin; *o++ = t.dest_count;
+    }
+  };
+  put(A.ptasks_ft, tasks_f);
+  put(A.ptasks_bt, tasks_b);
+  for (int e : A.pexpect_top) *expect++ = e;
+}
 double spllt_b200_wide_frac(void* akeep) { return AA(akeep)->wide_frac; }
 int spllt_b200_pipe_max_nrhs(void* akeep) { return AA(akeep)->pipe_max_nrhs; }
 void spllt_b200_pipe_sizes(void* akeep, long long* out4) {

@@ -200,3 +200,77 @@ def test_path_selection_follows_the_structure():
     row = np.concatenate([np.arange(j + 1, n + 1) for j in range(n)]).astype(np.int32)
     wide.analyse(n, ptr, row)
     assert wide.L.spllt_b200_wide_frac(wide.akeep) > 0.6 and wide.L.spllt_b200_pipe_max_nrhs(wide.akeep) == 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_lists(world):
+    """Multi-GPU solve (spllt_b200/dist.py): for every rank, the lists of its own subtrees and of
+    the shared upper tree replay without an unsatisfied wait -- forward: subtrees, (all-reduce),
+    upper tree with fresh counters; backward: upper tree, then the subtrees on the SAME flags --
+    and over all ranks every row of every node is swept exactly once (upper tree: once per rank)."""
+    n, ptr, row, val = M.poisson3d(22)
+    covered = None
+    for rank in range(world):
+        s = sp.SpLLT(nb=64, ncpu=world)
+        assert s.analyse(n, ptr, row) == 0
+        s.L.spllt_b200_partition_host(s.akeep, rank, world)
+        nn = s.nnodes
+        own = np.array([s.L.spllt_b200_node_owner(s.akeep, k + 1) for k in range(nn)])
+        tf, tb, nd, dest, nstrips, exp_own = s.pipe_tables()
+        tft, tbt, exp_top = s.pipe_top_tables()
+        m_, n_, sa, strip0, np_, exp_f, exp_b, pflag = nd.T
+        strip_node = np.repeat(np.arange(nn), np_)
+        assert set(tf[:, 0]) <= set(np.nonzero(own == rank)[0]) and set(tft[:, 0]) <= set(np.nonzero(own < 0)[0])
+        rows_done = [np.zeros(m_[k], np.int32) for k in range(nn)]
+
+        def forward(tasks, expect, in_list):
+            flags = np.zeros(nstrips, bool)
+            cnt = np.zeros(nstrips, np.int64)
+            for node, kind, r0, nrows, db, dc in tasks:
+                assert in_list[node]
+                if kind != BELOW:
+                    f = strip0[node] + (r0 if kind == DIAG else 0)
+                    assert flags[strip0[node]:f].all() and not flags[f] and cnt[f] == expect[f]
+                    flags[f] = True
+                    i = f - strip0[node]
+                    rows_done[node][i * PS:min((i + 1) * PS, n_[node])] += 1
+                if kind != DIAG:
+                    assert flags[strip0[node]:strip0[node] + np_[node]].all()
+                    d = dest[db:db + dc]
+                    d = d[in_list[strip_node[d]]]          # strips of other lists: summed by the all-reduce
+                    assert not flags[d].any()
+                    cnt[d] += 1
+                    lo, hi = (r0, r0 + nrows) if kind == BELOW else (n_[node], m_[node])
+                    rows_done[node][lo:hi] += 1
+            assert np.array_equal(cnt[in_list[strip_node]], expect[in_list[strip_node]])
+            return flags
+
+        def backward(tasks, in_list, flags):
+            cntb = np.zeros(nn, np.int64)
+            for node, kind, r0, nrows, db, dc in tasks:
+                assert in_list[node]
+                if kind != DIAG:
+                    assert flags[dest[db:db + dc]].all()        # incl. upper-tree strips raised by the previous launch
+                    cntb[node] += kind == BELOW
+                if kind != BELOW:
+                    i = r0 if kind == DIAG else 0
+                    f0 = strip0[node]
+                    if kind == DIAG and i == np_[node] - 1:
+                        assert cntb[node] == exp_b[node]
+                    assert flags[f0 + i + 1:f0 + np_[node]].all() and not flags[f0 + i]
+                    flags[f0 + i] = True
+            return flags
+
+        forward(tf, exp_own, own == rank)
+        forward(tft, exp_top, own < 0)
+        flags = backward(tbt, own < 0, np.zeros(nstrips, bool))
+        flags = backward(tb, own == rank, flags)
+        mine = (own == rank) | (own < 0)
+        assert flags[mine[strip_node]].all() and not flags[~mine[strip_node]].any()
+        for k in range(nn):
+            assert (rows_done[k] == (1 if mine[k] else 0)).all()
+        c = np.where(own == rank, 1, 0)
+        covered = c if covered is None else covered + c
+        if rank == 0:
+            top = own < 0
+    assert np.array_equal(covered + top, np.ones(nn, int))
