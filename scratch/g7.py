@@ -8,11 +8,13 @@ os.environ['SPLLT_B200_GRAPH'] = '0'
 L = sp.lib()
 st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 def ev(): return torch.cuda.Event(enable_timing=True)
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-nb = 512 if N <= 80 else 768
+EL = sys.argv[1].startswith('el') if len(sys.argv) > 1 else False
+N = int(sys.argv[1][2:] if EL else sys.argv[1]) if len(sys.argv) > 1 else 64
+nb = 768 if EL else (512 if N <= 80 else 768)
+os.environ.setdefault('SPLLT_B200_PIPE_MAX_NRHS', '8')
 modes = [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else "0,1,2,4,5,7,12,15".split(','))]
 tmodes = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [0]
-n, ptr, row, val = M.poisson3d(N)
+n, ptr, row, val = M.elasticity3d(N) if EL else M.poisson3d(N)
 xs = np.ones((n, 1)); b = M.matvec(n, ptr, row, val, np.asfortranarray(xs))
 s = sp.SpLLT(nb=nb, ncpu=1); s.analyse(n, ptr, row)
 dval = torch.tensor(val, device='cuda'); s.set_stream(st.cuda_stream)

@@ -109,11 +109,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 // experiment switches (PipeArgs::mode, SPLLT_B200_PIPE_MODE):
 //   1: fence.acq_rel.gpu instead of __threadfence() (MEMBAR.SC) before a flag / counter is raised
-//   2: waiters back off (nanosleep) in proportion to their distance from the critical path
+//   2: waiters do NOT back off (default: nanosleep in proportion to their distance from the critical path)
 //   4: poll with ld.relaxed (no L1 invalidation per poll); x is read with L2-coherent loads behind
 //      the control dependency   8: ... plus one fence.acq_rel after a successful poll
 //  16: no L2 prefetch of a task's rows at task start   32: strips wait on flags, not on the mailbox
-enum { M_FENCE_ACQREL = 1, M_BACKOFF = 2, M_POLL_RELAXED = 4, M_POLL_FENCE = 8, M_NO_PREFETCH = 16, M_NO_MAILBOX = 32, M_NO_MAILBOX_BWD = 64 };
+enum { M_FENCE_ACQREL = 1, M_NO_BACKOFF = 2, M_POLL_RELAXED = 4, M_POLL_FENCE = 8, M_NO_PREFETCH = 16, M_NO_MAILBOX = 32, M_NO_MAILBOX_BWD = 64 };
 __device__ __forceinline__ void fence_gpu(int mode) {
   if (mode & M_FENCE_ACQREL)
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -156,7 +156,7 @@ __device__ __forceinline__ int wait_run(const int* f, int dir, int limit, int la
       __syncwarp();
       return b == FULL ? 32 : __ffs(~b) - 1;
     }
-    if ((mode & M_BACKOFF) && dist > 1) __nanosleep(min(dist - 1, 16) * 200);
+    if (!(mode & M_NO_BACKOFF) && dist > 1) __nanosleep(min(dist - 1, 16) * 200);
   }
 }
 __device__ __forceinline__ void wait_count(const int* c, int expect, int mode) {
@@ -328,6 +328,7 @@ __device__ __forceinline__ void fwd_strip(const PNode& nd, int node, int i, bool
             empty |= mailbox_empty(x0[q]) | mailbox_empty(x1[q]);
           }
           if (!__any_sync(FULL, empty)) break;
+          if (!(a.mode & M_NO_BACKOFF) && i - j > 2) __nanosleep(min(i - j, 24) * 64);   // far from the front: poll rarely
         }
         ready = j + 1;
       }
@@ -423,6 +424,7 @@ __device__ __forceinline__ void fwd_below(const PNode& nd, int r0, int nrows, co
           empty |= mailbox_empty(x0[q]) | mailbox_empty(x1[q]);
         }
         if (!__any_sync(FULL, empty)) break;
+        if (!(a.mode & M_NO_BACKOFF)) __nanosleep(256);   // rows below a wide node are never on the critical chain of strips
       }
     }
 #pragma unroll
@@ -597,6 +599,7 @@ __device__ __forceinline__ void bwd_strip(const PNode& nd, int node, int i, bool
           // once the node's last strip has started publishing
           if (jj == 0) empty |= mailbox_empty(ld_mailbox(a.xm + (i64)(nd.sa + j * PS) * a.nrhs + c.rc0));
           if (!__any_sync(FULL, empty)) break;
+          if (!(a.mode & M_NO_BACKOFF) && j - i > 2) __nanosleep(min(j - i, 24) * 64);
         }
       }
       if (jj == 0 && bvalid) bpre = __ldcg(xg + (i64)brow * a.nrhs + bq);
