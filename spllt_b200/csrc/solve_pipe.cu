@@ -13,21 +13,33 @@
 //
 //   forward, node s with n columns, m rows, np = ceil(n/64) strips
 //     DIAG(s,i)   owner of rows [64i, 64i+64) of the diagonal block.  Left-looking: streams the
-//                 tiles L[strip i, strip j], j < i, as the x_j are published (flag per strip),
-//                 accumulates in registers (no atomics), solves the 64 x 64 diagonal block,
-//                 publishes x_i and raises flag (s,i).
-//     BELOW(s,c)  64 rows below the diagonal block: same streaming product over all np strips,
-//                 then xw[index[r]] -= sum (RED.ADD.F64) and one counter bump per ancestor node hit.
-//     DIAG(s,0) waits until the node's counter shows that every contribution has arrived.
-//   backward: the mirror image (gather only): BELOW chunks wait for the parent, gather
-//     xw[index[r]], add L^T y into the node's x (RED) and bump the node's counter; DIAG(s,i)
-//     streams L[strip j, strip i]^T x_j for j > i in decreasing j, then solves L_ii^T.
+//                 tiles L[strip i, strip j], j < i, as the x_j are published, accumulates in
+//                 registers (no atomics), multiplies by the precomputed INVERSE of the 64 x 64
+//                 diagonal block (k_invert_diag, once per factorization: a matrix-vector product
+//                 instead of a 64-step substitution on the critical chain), publishes x_i.
+//     BELOW(s,c)  rows below the diagonal block: the same streaming product, then
+//                 xw[index[r]] -= sum (RED.ADD.F64) and one counter bump per ancestor STRIP hit.
+//                 Nodes of <= 4 strips: x_s goes to shared memory once, chunks of up to 512 rows;
+//                 wider nodes: 64-row chunks that walk the strips as they are published.
+//     DIAG(s,i) reads its right-hand side once its strip's counter shows that every
+//     contribution to those 64 rows has landed (so a parent starts after its child's first chunk).
+//   backward: the mirror image (gather only): a BELOW chunk waits for the flags of the ancestor
+//     strips its rows map to, gathers xw[index[r]], adds L^T y into the node's x (RED) and bumps
+//     the node's counter; DIAG(s,i) streams L[strip j, strip i]^T x_j for j > i in decreasing j.
 //   nodes with n <= 64 and few rows are ONE fused task (SMALL).
+//
+// Synchronisation, all in HBM: a flag per strip (st after __threadfence), counters
+// (ld.acquire.gpu), and -- for the strip-to-strip chain inside a node -- a MAILBOX copy of x made
+// of self-validating 8-byte words (see ld_mailbox), which takes the membar, the flag and one
+// dependent load off every link of the chain.  Waiters far from the front back off (nanosleep).
 //
 // CTAs claim tasks from a global counter in list order; lists are topological, so a claimed
 // task only waits on tasks already claimed by running CTAs: no deadlock, no co-residency
 // requirement.  Every L entry is read exactly once per sweep, 512 contiguous bytes per row and
-// warp instruction, with the next tile's loads in flight while the warp polls for x_j.
+// warp instruction; HBM latency is taken by prefetch.global.L2 (a task's rows when it starts,
+// tiles two steps ahead), the register loads of a tile are issued while the warp polls for x_j.
+// Multi-GPU: the same kernels run on per-rank lists (own subtrees / shared upper tree), see
+// Engine::solve_phase.
 #include <cstdio>
 #include <cstdlib>
 
