@@ -484,14 +484,27 @@ __device__ __forceinline__ void fwd_below_fat(const PNode& nd, int r0, int nrows
   double2 t[RPW];
   if (!local) {
     // x_s (n <= FAT_NP * 64 values per right-hand side) -> shared memory, once
-    if (warp == 0) {
-      int ready = 0;
-      while (ready < np) ready += wait_run(c.flags + nd.strip0 + ready, 1, np - ready, lane, a.mode, 1);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < np * PS * RC; k += PT) {
-      const int col = k / RC, q = k - col * RC;
-      (pipe_sm + Sm<RC>::XS)[k] = (col < nd.n && q < c.nr) ? __ldcg(a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0 + q) : 0.0;
+    if (a.mode & M_NO_MAILBOX) {
+      if (warp == 0) {
+        int ready = 0;
+        while (ready < np) ready += wait_run(c.flags + nd.strip0 + ready, 1, np - ready, lane, a.mode, 1);
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < np * PS * RC; k += PT) {
+        const int col = k / RC, q = k - col * RC;
+        (pipe_sm + Sm<RC>::XS)[k] = (col < nd.n && q < c.nr) ? __ldcg(a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0 + q) : 0.0;
+      }
+    } else {   // every thread polls its own entries of the mailbox: no flag, no fence on the path
+      for (int k = threadIdx.x; k < np * PS * RC; k += PT) {
+        const int col = k / RC, q = k - col * RC;
+        double v = 0.0;
+        if (col < nd.n && q < c.nr) {
+          const double* mp = a.xm + (i64)(nd.sa + col) * a.nrhs + c.rc0 + q;
+          while (mailbox_empty(v = ld_mailbox(mp))) {
+          }
+        }
+        (pipe_sm + Sm<RC>::XS)[k] = v;
+      }
     }
     __syncthreads();
   }
@@ -672,7 +685,17 @@ __device__ __forceinline__ void bwd_below(const PNode& nd, int r0, int nrows, co
     __syncthreads();   // rh may still be read by the previous pass / task
     for (int k = tid; k < PS * RC; k += PT) {
       const int r = k / RC, q = k - r * RC;
-      (pipe_sm + Sm<RC>::RH)[k] = (r < cnt && q < c.nr) ? __ldcg(a.xw + (i64)idx[r] * a.nrhs + c.rc0 + q) : 0.0;
+      double v = 0.0;
+      if (r < cnt && q < c.nr) {
+        if (a.mode & M_NO_MAILBOX_BWD) {
+          v = __ldcg(a.xw + (i64)idx[r] * a.nrhs + c.rc0 + q);   // the task waited for the ancestors' flags
+        } else {   // poll the ancestor's published value itself
+          const double* mp = a.xm + (i64)idx[r] * a.nrhs + c.rc0 + q;
+          while (mailbox_empty(v = ld_mailbox(mp))) {
+          }
+        }
+      }
+      (pipe_sm + Sm<RC>::RH)[k] = v;
     }
     __syncthreads();
     if (c.tr && tid == 0 && p == 0) c.tr[1] = gtime();
@@ -763,7 +786,9 @@ __global__ void __launch_bounds__(PT, RC == 1 ? PIPE_OCC : 1) k_solve_pipe(const
     } else {
       if (tk.kind != P_DIAG) {
         // every ancestor strip this task's rows map to has published its x
-        for (int k = tid; k < tk.dest_count; k += PT) wait_count(c.flags + a.dest[tk.dest_begin + k], 1, a.mode);
+        // (with the mailbox the gather itself waits, value by value)
+        if (a.mode & M_NO_MAILBOX_BWD)
+          for (int k = tid; k < tk.dest_count; k += PT) wait_count(c.flags + a.dest[tk.dest_begin + k], 1, a.mode);
         bwd_below<RC>(nd, rb0, rb1 - rb0, a, c);
         if (c.tr && tid == 0 && tk.kind == P_BELOW) c.tr[2] = gtime();
         if (tk.kind == P_SMALL) fence_gpu(a.mode);   // own REDs, re-read by this CTA right below
