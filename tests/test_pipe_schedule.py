@@ -274,3 +274,89 @@ def test_multi_gpu_lists(world):
         if rank == 0:
             top = own < 0
     assert np.array_equal(covered + top, np.ones(nn, int))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_gpu_lists_replayed_numerically(world):
+    """The multi-GPU solve in numpy: every rank executes its own lists on its own copy of the work
+    vector, the copies are summed where the real code all-reduces, and the result solves A x = b."""
+    nb = 48
+    n, ptr, row, val = M.poisson3d(14)
+    ranks = []
+    for rank in range(world):
+        s = sp.SpLLT(nb=nb, ncpu=world)
+        assert s.analyse(n, ptr, row) == 0
+        s.L.spllt_b200_partition_host(s.akeep, rank, world)
+        ranks.append(s)
+    s0 = ranks[0]
+    sptr, sparent, rptr, rlist = s0.symbolic()
+    nn = s0.nnodes
+    o = Oracle(n, ptr, row, s0.order, sptr, sparent, rptr, rlist, nb, ncpu=world)
+    o.factor(val, 1)
+    fo = o.factor_entries()
+    nd = s0.pipe_tables()[2]
+    m_, n_, sa = nd[:, 0], nd[:, 1], nd[:, 2]
+    Ls, pos = [], 0
+    for k in range(nn):
+        L = np.zeros((m_[k], n_[k]))
+        for c0 in range(0, n_[k], nb):
+            w, h = min(nb, n_[k] - c0), m_[k] - c0
+            L[c0:, c0:c0 + w] = fo[pos:pos + h * w].reshape(h, w)
+            pos += h * w
+        L[:n_[k], :n_[k]] = np.tril(L[:n_[k], :n_[k]])
+        Ls.append(L)
+    idx = [rlist[rptr[k] - 1:rptr[k + 1] - 1] - 1 for k in range(nn)]
+    col2node = np.repeat(np.arange(nn), n_)
+    xs = np.asfortranarray(1.0 + 0.5 * np.sin(np.arange(n)))[:, None]
+    b = np.asfortranarray(M.matvec(n, ptr, row, val, np.asfortranarray(xs)))
+    porder = np.argsort(s0.order[:n] - 1)
+
+    def fwd(xw, tasks):
+        for node, kind, r0, nrows, db, dc in tasks:
+            L, a = Ls[node], sa[node]
+            if kind != BELOW:
+                i = r0 if kind == DIAG else 0
+                sl = slice(i * PS, min((i + 1) * PS, n_[node]))
+                rhs = xw[a + sl.start:a + sl.stop] - L[sl, :sl.start] @ xw[a:a + sl.start]
+                xw[a + sl.start:a + sl.stop] = np.linalg.solve(L[sl, sl], rhs)
+            if kind != DIAG:
+                lo, hi = (r0, r0 + nrows) if kind == BELOW else (n_[node], m_[node])
+                xw[idx[node][lo:hi]] -= L[lo:hi, :] @ xw[a:a + n_[node]]
+
+    def bwd(xw, tasks):
+        for node, kind, r0, nrows, db, dc in tasks:
+            L, a = Ls[node], sa[node]
+            if kind != DIAG:
+                lo, hi = (r0, r0 + nrows) if kind == BELOW else (n_[node], m_[node])
+                xw[a:a + n_[node]] -= L[lo:hi, :].T @ xw[idx[node][lo:hi]]
+            if kind != BELOW:
+                i = r0 if kind == DIAG else 0
+                sl = slice(i * PS, min((i + 1) * PS, n_[node]))
+                rhs = xw[a + sl.start:a + sl.stop] - L[sl.stop:n_[node], sl].T @ xw[a + sl.stop:a + n_[node]]
+                xw[a + sl.start:a + sl.stop] = np.linalg.solve(L[sl, sl].T, rhs)
+
+    keep, copies = [], []
+    for rank, s in enumerate(ranks):
+        own = np.array([s.L.spllt_b200_node_owner(s.akeep, k + 1) for k in range(nn)])
+        k_ = (own[col2node] == rank) | ((own[col2node] < 0) & (rank == 0))
+        keep.append(k_)
+        xw = b[porder, :].copy()
+        xw[~k_] = 0.0                                        # phase 0
+        fwd(xw, s.pipe_tables()[0])                          # phase 1
+        copies.append(xw)
+    total = sum(copies)                                       # all-reduce
+    copies = []
+    for rank, s in enumerate(ranks):
+        xw = total.copy()
+        tft, tbt, _ = s.pipe_top_tables()
+        fwd(xw, tft)                                          # phase 2
+        bwd(xw, tbt)                                          # phase 3
+        bwd(xw, s.pipe_tables()[1])                           # phase 4
+        xw[~keep[rank]] = 0.0
+        copies.append(xw)
+    xw = sum(copies)                                          # all-reduce
+    x = np.empty_like(xw)
+    x[porder, :] = xw
+    ok, err = chkerr(n, ptr, row, val, np.asfortranarray(x), b)
+    assert ok == 1 and err.max() <= 1e-14, err
+    assert np.abs(x - xs).max() <= 1e-10
