@@ -2,6 +2,7 @@
 // reference by interfaces/C/spllt_data_ciface.F90:89-780) plus the B200 additions of
 // include/spllt_b200.h.  No torch types, no exceptions across the boundary.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -80,12 +81,22 @@ void analyse_impl(void** akeep, void** fkeep, spllt_options_t* options, int n, c
   fk->eng.release();
   ak->A = std::make_shared<Analysis>();
   Analysis& A = *ak->A;
+  // SPLLT_B200_ANALYSE_TIMING=1: phase timers of the host analysis on stderr (the reference's
+  // timer_mod, src/timer_mod.F90:76-547, reduced to what the host still does)
+  const bool timing = env_int("SPLLT_B200_ANALYSE_TIMING", 0) != 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   int rc = build_analysis(n, ptr, row, options->nb, options->nemin, options->ncpu, options->prune_tree != 0, ordering,
                           ordering == ORDER_USER ? order : nullptr, A);
+  const double t1 = now();
   A.min_width_blas = options->min_width_blas;
   if (rc == 0 && n > 0) {
     build_factor_schedule(A, env_int("SPLLT_B200_TILE_L_MIN", 128));
+    const double t2 = now();
     build_solve_schedule(A);
+    if (timing)
+      fprintf(stderr, "spllt_b200 analyse: ordering + symbolic + tables %.3f s, factor schedule %.3f s, solve schedule %.3f s\n",
+              t1 - t0, t2 - t1, now() - t2);
     if (order)
       for (int i = 0; i < n; ++i) order[i] = A.sym.order[i];
   }
