@@ -325,7 +325,9 @@ def main():
         roofline = {"bound": "tensor", "kernel": "k_tile_tma<64,2> (persistent TMA + DMMA.8x8x4, 128x64 tiles) + "
                                                  "k_tile<64,64,32,32,2> (small launches)",
                     "achieved": achieved, "peak": peaks["dmma"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["dmma"] if peaks["dmma"] else None, "traffic": traffic,
+                    "frac": achieved / peaks["dmma"] if peaks["dmma"] else None,
+                    # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full); details beside it
+                    "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
                     "peak_source": "own register-resident mma.sync.m8n8k4.f64 probe on 148 SMs, measured in this "
                                    "run (MEASURED_PEAKS.json has no FP64 figure); DFMA probe = %.1f TFLOP/s" % peaks["dfma"],
                     "flops_per_launch": tile_flops / max(n_tile_launch, 1), "launches": n_tile_launch,
