@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the SpLLT numerical phase on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-A "step" is one numerical factorization (spllt_factor + spllt_wait) of BASELINE.json's
-configs[1]: 3D Poisson 7-point 64^3 (n = 262144), nb = 512, METIS nested dissection, nemin = 32.
+A "step" is one numerical factorization (spllt_factor + spllt_wait) of BASELINE.json's headline
+configuration, configs[2]: 3D Poisson 7-point 100^3 (n = 1 000 000), nb = 768, METIS nested
+dissection, nemin = 32 -- the configuration the metric is quoted on at 1/2/4/8 GPUs; it fits one GPU
+(7.8 GB of factor).  Protocol of the reference's own benchmark scripts
+(aux/run_tests_pde_job.sh:77-90: analyse once, then time the factorization and the solve).
+
 `value` = factor GFLOP/s with `val` already resident in HBM (flops = the reference's own count,
 sum_nodes sum_j (m-n+j)^2, src/spllt_analyse_mod.F90:1013-1021); `e2e` = the same metric through
 the reference-facing C ABI with HOST buffers (spllt_factor copies val H2D, spllt_wait, pivot flag
-read back).  The solve (seconds per RHS, achieved HBM GB/s) is timed separately and reported in
-`solve`.  Prints ONE JSON line on rank 0.
+read back).  `roofline` = the DMMA tile kernels against the measured FP64 tensor peak
+(ALGORITHMIC flops: 2 K per updated entry of the lower triangle; the issued/padded count is
+reported beside it); `roofline_solve` = the triangular solves against the measured HBM bandwidth;
+`extra` = BASELINE configs[1] (64^3 factor + solve) and configs[4] (80^3 solve, nrhs 1/16/64).
+Prints ONE JSON line on rank 0.
 
---impl reference times the CPU restatement of the reference's OpenMP build (oracle/, OpenMP tasks
-+ sequential OpenBLAS) on the host cores, same config and metric.
+--impl reference times the CPU restatement of the reference's OpenMP build (oracle/: OpenMP tasks +
+sequential OpenBLAS; the Fortran reference cannot be compiled in this image) on all host cores,
+same config / metric; a step is a bounded sample of the factorization (see run_reference).  That
+arm never imports or loads the product (spllt_b200 / libspllt_b200.so).
 """
 import argparse
 import ctypes as C
+import importlib.util
 import json
 import os
 import subprocess
@@ -37,6 +47,8 @@ WORKLOADS = {
     "el3d60": ("elasticity3d", (60,), 768, "3D elasticity 27-point 3-dof 60^3 (n=648000), nb=768"),
     "p3d32": ("poisson3d", (32,), 256, "3D Poisson 7-point 32^3 (n=32768), nb=256 [smoke size]"),
 }
+HEADLINE = "p3d100"
+REF_BUDGET_S = 200.0     # the whole --impl reference run (all steps) aims at this much CPU wall time
 
 
 def parse():
@@ -45,16 +57,32 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("SPLLT_BENCH_WORKLOAD", "p3d64"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("SPLLT_BENCH_WORKLOAD", HEADLINE), choices=sorted(WORKLOADS))
     ap.add_argument("--nrhs", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 64^3 / 80^3 side measurements")
     return ap.parse_args()
 
 
+def matrices_module():
+    """spllt_b200/matrices.py loaded by path (pure numpy): the CPU arm must not import the product package."""
+    spec = importlib.util.spec_from_file_location("spllt_matrices", os.path.join(ROOT, "spllt_b200", "matrices.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 def make_matrix(workload):
-    from spllt_b200 import matrices as M
+    M = matrices_module()
     gen, a, nb, desc = WORKLOADS[workload]
     return getattr(M, gen)(*a), nb, desc
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
 class ClockSampler:
@@ -108,22 +136,57 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_factor(mat, nb, nthreads, runs):
-    """The CPU arm: oracle port of the reference's OMP build (OpenMP tasks + sequential OpenBLAS)."""
-    import spllt_b200 as sp
-    from oracle.oracle import Oracle
-    n, ptr, row, val = mat
-    s = sp.SpLLT(nb=nb, ncpu=nthreads)     # the reference prunes the tree for ncpu workers
-    s.analyse(n, ptr, row)
-    sptr, sparent, rptr, rlist = s.symbolic()
-    o = Oracle(n, ptr, row, s.order, sptr, sparent, rptr, rlist, nb, ncpu=nthreads)
-    flops = s.num_flops
-    times = []
-    for _ in range(runs):
+# ------------------------------------------------------------------------------------ CPU arm
+class CpuReference:
+    """The restated reference (oracle/) on the host cores.  Symbolic inputs come from the SSIDS
+    stand-in compiled into oracle/libssids_standin.so -- nothing of the product is loaded."""
+
+    def __init__(self, mat, nb, nthreads):
+        from oracle import oracle as O
+        n, ptr, row, val = mat
+        self.val, self.nthreads = val, nthreads
+        order, sptr, sparent, rptr, rlist = O.symbolic(n, ptr, row, nemin=32)
+        # the reference prunes the tree for ncpu workers (src/spllt_analyse_mod.F90:297)
+        self.o = O.Oracle(n, ptr, row, order, sptr, sparent, rptr, rlist, nb, ncpu=nthreads)
+        w = self.o.weight()
+        nn = len(sptr) - 1
+        own = w[:-1].astype(np.float64).copy()
+        par = np.asarray(sparent) - 1
+        np.subtract.at(own, par[par < nn], w[:-1][par < nn].astype(np.float64))
+        self.cum = np.cumsum(own)          # flops of nodes 1..k (postorder prefix)
+        self.small = self.o.small()
+        self.nn = nn
+        self.total = float(self.cum[-1]) if nn else 0.0
+
+    def prefix_for(self, frac):
+        """last node of the smallest postorder prefix holding >= frac of the flops that does not
+        cut a pruned subtree; (last_node, flops of the prefix)"""
+        if frac >= 0.9 or self.nn == 0:
+            return self.nn, self.total
+        ok = np.nonzero((self.cum >= frac * self.total) & (self.small >= 0))[0]
+        last = int(ok[0]) + 1 if len(ok) else self.nn
+        return last, float(self.cum[last - 1])
+
+    def run(self, last_node):
         t = time.perf_counter()
-        o.factor(val, nthreads)
-        times.append(time.perf_counter() - t)
-    return flops, times, s, o
+        self.o.factor_prefix(self.val, self.nthreads, last_node)
+        return time.perf_counter() - t
+
+    def sampled(self, nsteps_total, budget_s):
+        """Chooses the sample: one calibration run on a 5 % prefix gives a rate; the sample is the
+        largest prefix (whole subtrees + the upper-tree nodes above them, in postorder) such that
+        nsteps_total steps fit the budget.  Returns (last_node, flops, description)."""
+        last, fl = self.prefix_for(0.05)
+        dt = self.run(last)            # also allocates the factor storage (not timed later)
+        dt = min(dt, self.run(last))
+        rate = fl / max(dt, 1e-9)
+        frac = min(1.0, budget_s * rate / (max(nsteps_total, 1) * max(self.total, 1.0)))
+        last, fl = self.prefix_for(frac)
+        if last >= self.nn:
+            return self.nn, self.total, "one full factorization of the workload per step"
+        return last, fl, ("bounded sample per step: nodes 1..%d of %d in postorder (whole subtrees and the "
+                          "upper-tree nodes above them) = %.1f%% of the factorization's flops, all of their "
+                          "init / factorize / update tasks" % (last, self.nn, 100.0 * fl / self.total))
 
 
 def run_reference(args, rank, world):
@@ -131,23 +194,163 @@ def run_reference(args, rank, world):
         return
     mat, nb, desc = make_matrix(args.workload)
     cores = os.cpu_count() or 1
-    flops, times, s, o = cpu_reference_factor(mat, nb, cores, args.warmup + args.steps)
-    t = times[args.warmup:]
-    sec = float(np.mean(t))
-    val = flops / sec / 1e9
+    ref = CpuReference(mat, nb, cores)
+    last, fl, what = ref.sampled(args.warmup + args.steps, REF_BUDGET_S)
+    for _ in range(args.warmup):
+        ref.run(last)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.run(last)
+    sec = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = fl / sec / 1e9
+    sample = ("%s; OpenMP tasks on %d threads + sequential OpenBLAS (restated reference OMP build; the Fortran "
+              "reference cannot be compiled in this image)" % (what, cores))
     out = {
         "impl": "reference", "metric": "factor_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc + ", METIS nested dissection, nemin=32", "flops_per_step": flops},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-                         "sample": "full factorization of the workload per step, OpenMP tasks on %d threads + "
-                                   "sequential OpenBLAS (restated reference OMP build; the Fortran reference "
-                                   "cannot be compiled in this image)" % cores},
+        "config": {"workload": desc + ", METIS nested dissection, nemin=32", "flops_per_step": int(fl),
+                   "flops_full_factorization": int(ref.total)},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+class Bench:
+    def __init__(self, args, rank, world, local):
+        import torch
+        self.torch = torch
+        self.args, self.rank, self.world, self.local = args, rank, world, local
+        import spllt_b200 as sp
+        from spllt_b200 import dist as spdist
+        self.sp, self.spdist = sp, spdist
+        self.L = sp.lib()
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        self.sptr_ = C.c_void_p(self.stream.cuda_stream)
+        self.hbm, self.hbm_src = hbm_peak()
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def maxrank(self, ms):
+        if self.world > 1:
+            import torch.distributed as dist
+            t = self.torch.tensor([ms], device="cuda", dtype=self.torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def peaks(self):
+        out = {}
+        for kind, nme in ((0, "dmma"), (1, "dfma")):
+            self.L.spllt_b200_peak_probe(kind, 2000, self.sptr_)
+            self.torch.cuda.synchronize()
+            best = 0.0
+            for _ in range(3):
+                a, b = self.ev(), self.ev()
+                a.record()
+                fl = self.L.spllt_b200_peak_probe(kind, 20000, self.sptr_)
+                b.record()
+                self.torch.cuda.synchronize()
+                best = max(best, fl / a.elapsed_time(b) / 1e9)
+            out[nme] = best
+        return out
+
+    def setup(self, workload):
+        mat, nb, desc = make_matrix(workload)
+        n, ptr, row, val = mat
+        solver = self.spdist.DistSpLLT(nb=nb, rank=self.rank, world=self.world, stream=self.stream)
+        t0 = time.perf_counter()
+        solver.analyse(n, ptr, row)
+        t_analyse = time.perf_counter() - t0
+        return mat, nb, desc, solver, t_analyse
+
+    def time_factor(self, solver, d_val, steps, warmup):
+        for _ in range(warmup):
+            solver.factor_dev(d_val)
+        self.barrier()
+        a, b = self.ev(), self.ev()
+        self.barrier()
+        a.record()
+        for _ in range(steps):
+            solver.factor_dev(d_val)
+        b.record()
+        self.barrier()
+        return self.maxrank(a.elapsed_time(b) / steps)
+
+    def time_e2e(self, solver, hv, steps):
+        for _ in range(2):
+            solver.factor_host(hv)
+            solver.wait()
+        self.barrier()
+        a, b = self.ev(), self.ev()
+        a.record()
+        for _ in range(steps):
+            solver.factor_host(hv)          # spllt_factor: H2D copy of val + factorization
+            solver.wait()                   # spllt_wait
+            _ = solver.pivot_flag()         # D2H read of the step's result
+        b.record()
+        self.barrier()
+        return self.maxrank(a.elapsed_time(b) / steps)
+
+    def solve_bytes(self, s, n, nrhs):
+        # SURVEY 8(d): per sweep 8 nnz(L) + 2*8*n*nrhs + 3*8*sum(m-n)*nrhs; fwd + bwd = 2x
+        sptr, sparent, rptr, rlist = s.symbolic()
+        upd = int(np.sum(np.diff(rptr) - np.diff(sptr)))
+        return 2 * (8 * s.num_factor + 16 * n * nrhs + 24 * upd * nrhs)
+
+    def time_solve(self, solver, mat, nrhs, reps):
+        """seconds per solve (fwd + bwd, nrhs right-hand sides), backward errors, one solution"""
+        torch = self.torch
+        n, ptr, row, val = mat
+        M = matrices_module()
+        xs = np.asfortranarray(np.tile(np.arange(1.0, nrhs + 1), (n, 1)))
+        if nrhs > 1:   # SURVEY 8(d): seeded random right-hand sides beside the reference's x = r convention
+            rng = np.random.Generator(np.random.PCG64(20261018))
+            xs[:, 1::2] = rng.standard_normal((n, xs[:, 1::2].shape[1]))
+        rhs = np.asfortranarray(M.matvec(n, ptr, row, val, xs))
+        d_rhs = [torch.tensor(rhs.T.copy(), device="cuda") for _ in range(reps + 2)]
+        for d in d_rhs[:2]:
+            solver.solve_dev(d, nrhs)
+        self.barrier()
+        a, b = self.ev(), self.ev()
+        a.record()
+        for d in d_rhs[2:]:
+            solver.solve_dev(d, nrhs)
+        b.record()
+        self.barrier()
+        ms = self.maxrank(a.elapsed_time(b) / reps)
+        x = np.asfortranarray(d_rhs[2].cpu().numpy().T)
+        ok, err = self.sp.chkerr(n, ptr, row, val, x, rhs)
+        fwd_err = float(np.abs(x - xs).max() / np.abs(xs).max())
+        return ms, ok, err, fwd_err, d_rhs[0]
+
+    def solve_report(self, solver, mat, nrhs, reps):
+        s = solver.local
+        n = mat[0]
+        ms, ok, err, fwd_err, d0 = self.time_solve(solver, mat, nrhs, reps)
+        sbytes = self.solve_bytes(s, n, nrhs)
+        if self.world > 1:
+            path = solver.solve_path()
+        elif nrhs <= self.L.spllt_b200_pipe_max_nrhs(s.akeep) and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET"):
+            path = "persistent pipelined kernels k_solve_pipe<fwd>/<bwd> (64-row strips, flags in HBM)"
+        else:
+            path = "level-set launches k_fwd_diag/k_fwd_upd/k_bwd_upd/k_bwd_diag"
+        rep = {"nrhs": nrhs, "seconds": ms / 1e3, "seconds_per_rhs": ms / 1e3 / nrhs, "algorithmic_bytes": sbytes,
+               "achieved_gbs": sbytes / ms / 1e6, "hbm_peak_gbs": self.hbm,
+               "frac_of_hbm": sbytes / ms / 1e6 / self.hbm / max(self.world, 1), "path": path,
+               "scaled_backward_error_max": float(err.max()), "rhs_ok": int(ok), "forward_error_max": fwd_err}
+        return rep, d0
 
 
 def main():
@@ -161,163 +364,76 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import spllt_b200 as sp
-    from spllt_b200 import dist as spdist
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L = sp.lib()
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    sptr_ = C.c_void_p(stream.cuda_stream)
+    B = Bench(args, rank, world, local)
+    L = B.L
+    peaks = B.peaks()
+    warm = max(args.warmup, 3)
 
-    def ev():
-        return torch.cuda.Event(enable_timing=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    mat, nb, desc = make_matrix(args.workload)
+    mat, nb, desc, solver, t_analyse = B.setup(args.workload)
     n, ptr, row, val = mat
-    solver = spdist.DistSpLLT(nb=nb, rank=rank, world=world, stream=stream)
-    t0 = time.perf_counter()
-    solver.analyse(n, ptr, row)
-    t_analyse = time.perf_counter() - t0
     s = solver.local
     flops = s.num_flops
     d_val = torch.tensor(val, device="cuda")
     h_val = torch.tensor(val).pin_memory()
-
-    # ---------------- FP64 tensor-pipe peak (no FP64 figure in MEASURED_PEAKS.json)
-    peaks = {}
-    for kind, nme in ((0, "dmma"), (1, "dfma")):
-        L.spllt_b200_peak_probe(kind, 2000, sptr_)
-        torch.cuda.synchronize()
-        best = 0.0
-        for _ in range(3):
-            a, b = ev(), ev()
-            a.record()
-            fl = L.spllt_b200_peak_probe(kind, 20000, sptr_)
-            b.record()
-            torch.cuda.synchronize()
-            best = max(best, fl / a.elapsed_time(b) / 1e9)
-        peaks[nme] = best
+    cfg_more = {"nnz_L": int(s.num_factor), "multi_gpu": solver.describe(),
+                "factor_gb": L.spllt_b200_arena_doubles(s.akeep) * 8 / 1e9}
+    launches_per_factor = int(solver.launches_per_factor())
 
     # ---------------- timed region: K factorizations, val resident in HBM
-    for _ in range(max(args.warmup, 3)):
-        solver.factor_dev(d_val)
-    barrier()
     clocks = ClockSampler(local)
     clocks.start()
-    a, b = ev(), ev()
-    barrier()
-    a.record()
-    for _ in range(args.steps):
-        solver.factor_dev(d_val)
-    b.record()
-    barrier()
-    ms = a.elapsed_time(b) / args.steps
+    ms = B.time_factor(solver, d_val, args.steps, warm)
     clk = clocks.stop()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     pivot = solver.pivot_flag()
-    work_units = solver.work_multiplier()      # 1 for the distributed factorization, N for replicas
-    value = work_units * flops / ms / 1e6
+    value = flops / ms / 1e6
 
     # ---------------- e2e: reference-facing C ABI with host buffers
-    hv = h_val.numpy()
-    for _ in range(2):
-        solver.factor_host(hv)
-        solver.wait()
-    barrier()
-    a2, b2 = ev(), ev()
-    a2.record()
-    for _ in range(args.steps):
-        solver.factor_host(hv)          # spllt_factor: H2D copy of val + factorization
-        solver.wait()                   # spllt_wait
-        _ = solver.pivot_flag()         # D2H read of the step's result
-    b2.record()
-    barrier()
-    ms_e2e = a2.elapsed_time(b2) / args.steps
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    e2e = {"value": work_units * flops / ms_e2e / 1e6, "unit": "GFLOP/s", "ms_per_step": ms_e2e,
+    ms_e2e = B.time_e2e(solver, h_val.numpy(), args.steps)
+    e2e = {"value": flops / ms_e2e / 1e6, "unit": "GFLOP/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": int(val.nbytes), "d2h_bytes_per_step": 4}
 
-    # ---------------- solve: seconds per RHS, achieved HBM bandwidth (single-GPU path)
-    solve = None
-    parity = None
-    if True:
-        nrhs = args.nrhs
-        from spllt_b200 import matrices as M
-        xs = np.asfortranarray(np.tile(np.arange(1.0, nrhs + 1), (n, 1)))
-        rhs = np.asfortranarray(M.matvec(n, ptr, row, val, xs))
-        reps = max(args.steps, 3)
-        d_rhs = [torch.tensor(rhs.T.copy(), device="cuda") for _ in range(reps + 2)]
-        for d in d_rhs[:2]:
-            solver.solve_dev(d, nrhs)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        a3, b3 = ev(), ev()
-        a3.record()
-        for d in d_rhs[2:]:
-            solver.solve_dev(d, nrhs)
-        b3.record()
-        torch.cuda.synchronize()
-        ms_solve = a3.elapsed_time(b3) / reps
-        if world > 1:
-            t = torch.tensor([ms_solve], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_solve = float(t.item())
-        x = np.asfortranarray(d_rhs[2].cpu().numpy().T)
-        ok, err = sp.chkerr(n, ptr, row, val, x, rhs)
-        nfac = s.num_factor
-        sptr, sparent, rptr, rlist = s.symbolic()
-        upd = int(np.sum(np.diff(rptr) - np.diff(sptr)))
-        # SURVEY 8(d): per sweep 8 nnz(L) + 2*8*n*nrhs + 3*8*sum(m-n)*nrhs; fwd + bwd = 2x
-        sbytes = 2 * (8 * nfac + 16 * n * nrhs + 24 * upd * nrhs)
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] \
-            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        if world > 1:
-            path = ("multi-GPU: persistent pipelined kernels on the rank's subtrees, upper tree redundantly, "
-                    "two NCCL all-reduces of the work vector")
-        elif nrhs <= L.spllt_b200_pipe_max_nrhs(s.akeep) and not os.environ.get("SPLLT_B200_SOLVE_LEVELSET"):
-            path = "persistent pipelined kernels k_solve_pipe<fwd>/<bwd> (64-row strips, flags in HBM)"
-        else:
-            path = "level-set launches k_fwd_diag/k_fwd_upd/k_bwd_upd/k_bwd_diag"
-        solve = {"nrhs": nrhs, "seconds": ms_solve / 1e3, "seconds_per_rhs": ms_solve / 1e3 / nrhs,
-                 "algorithmic_bytes": sbytes, "achieved_gbs": sbytes / ms_solve / 1e6, "hbm_peak_gbs": hbm_peak,
-                 "frac_of_hbm": sbytes / ms_solve / 1e6 / hbm_peak / max(world, 1),
-                 "launches": int(L.spllt_b200_solve_launches(s.fkeep, 0)) if world == 1 else 8, "path": path}
-        if world == 1:
-            solve["profile_ms"] = s.profile_solve(d_rhs[0].data_ptr(), nrhs)
-            tpath = os.path.join(ROOT, "profiles", "solve_traffic.json")
-            if os.path.exists(tpath):   # dram bytes of k_solve_pipe<fwd> + <bwd> from one ncu --set full capture
-                solve["traffic"] = json.load(open(tpath))
-        parity = {"scaled_backward_error_max": float(err.max()), "rhs_ok": int(ok), "nrhs": nrhs, "tol": 1e-14,
-                  "forward_error_max": float(np.abs(x - xs).max() / np.abs(xs).max()), "pivot_flag": int(pivot)}
+    # ---------------- solve: seconds per RHS, achieved HBM bandwidth
+    reps = max(min(args.steps, 10), 3)
+    solve, d0 = B.solve_report(solver, mat, args.nrhs, reps)
+    solve["launches"] = int(L.spllt_b200_solve_launches(s.fkeep, 0)) if world == 1 else None
+    roofline_solve = {"bound": "hbm", "kernel": "k_solve_pipe<1,fwd> + k_solve_pipe<1,bwd> (one launch per sweep)"
+                      if "pipelined" in solve["path"] else solve["path"],
+                      "achieved": solve["achieved_gbs"] / max(world, 1), "peak": B.hbm, "unit": "GB/s",
+                      "frac": solve["frac_of_hbm"], "peak_source": B.hbm_src,
+                      "bytes_per_solve": solve["algorithmic_bytes"], "traffic": None}
+    if world == 1:
+        solve["profile_ms"] = s.profile_solve(d0.data_ptr(), args.nrhs)
+        tpath = os.path.join(ROOT, "profiles", "solve_traffic.json")
+        if os.path.exists(tpath):   # dram bytes of k_solve_pipe<fwd> + <bwd> from one ncu --set full capture
+            tr = json.load(open(tpath))
+            solve["traffic"] = tr
+            if tr.get("workload") == args.workload:
+                roofline_solve["traffic"] = tr.get("dram_bytes_read", 0) + tr.get("dram_bytes_write", 0)
+    parity = {"scaled_backward_error_max": solve["scaled_backward_error_max"], "rhs_ok": solve["rhs_ok"],
+              "nrhs": args.nrhs, "tol": 1e-14, "forward_error_max": solve["forward_error_max"],
+              "pivot_flag": int(pivot)}
+    if world > 1:
+        # the distributed factor against a single-GPU factorization of the same matrix on every rank
+        # (entries of the nodes the rank holds), outside the timed region
+        parity["factor_vs_single_gpu"] = solver.compare_with_single_gpu(d_val)
 
-    # ---------------- roofline of the dominant kernel (128x128 DMMA tile update)
+    # ---------------- roofline of the dominant kernel (DMMA tile updates)
     roofline = None
     if rank == 0:
-        prof = s.profile_factor(d_val.data_ptr())
+        prof = solver.profile_factor(d_val)
         bd = np.zeros(4, dtype=np.int64)
         L.spllt_b200_launch_breakdown(s.akeep, bd.ctypes.data_as(C.POINTER(C.c_longlong)))
-        tile_flops = float(L.spllt_b200_tile_flops(s.akeep))          # flops issued by tile kernels
+        issued = float(L.spllt_b200_tile_flops(s.akeep))            # padded tiles, masked halves included
+        algo = float(L.spllt_b200_tile_flops_algo(s.akeep))         # 2 K per updated entry (i >= j)
         tile_ms = prof["tile_s"] + prof["tile_l"]
-        n_tile_launch = int(bd[2] + bd[3])
-        achieved = tile_flops / tile_ms / 1e9 if tile_ms > 0 else 0.0  # TFLOP/s
+        n_tile_launch = int(bd[1] + bd[2])
+        achieved = algo / tile_ms / 1e9 if tile_ms > 0 else 0.0      # TFLOP/s
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
@@ -326,59 +442,65 @@ def main():
                                                  "k_tile<64,64,32,32,2> (small launches)",
                     "achieved": achieved, "peak": peaks["dmma"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["dmma"] if peaks["dmma"] else None,
+                    "flops": "algorithmic: 2*K per destination entry with i >= j of every tile update "
+                             "(what the reference's dgemm/dsyrk calls count); this rank's tiles",
+                    "achieved_issued": issued / tile_ms / 1e9 if tile_ms > 0 else 0.0,
+                    "issued_over_algorithmic": issued / algo if algo else None,
                     # bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full); details beside it
                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_detail": traffic,
                     "peak_source": "own register-resident mma.sync.m8n8k4.f64 probe on 148 SMs, measured in this "
                                    "run (MEASURED_PEAKS.json has no FP64 figure); DFMA probe = %.1f TFLOP/s" % peaks["dfma"],
-                    "flops_per_launch": tile_flops / max(n_tile_launch, 1), "launches": n_tile_launch,
+                    "flops_per_launch": algo / max(n_tile_launch, 1), "launches": n_tile_launch,
                     "avg_launch_ms": tile_ms / max(n_tile_launch, 1),
-                    "share_of_step": tile_ms / sum(prof.values()),
+                    "share_of_step": tile_ms / max(sum(prof.values()), 1e-9),
                     "profile_ms": prof, "whole_factor_frac_of_peak": value / 1e3 / peaks["dmma"] / max(world, 1)}
 
-    # ---------------- CPU baseline (rank 0, N = 1 only)
+    # ---------------- side measurements: BASELINE configs[1] and configs[4] (N = 1 only)
+    extra = None
+    if world == 1 and not args.no_extra and args.workload == HEADLINE:
+        extra = {}
+        del solver, s
+        torch.cuda.empty_cache()
+        for wl, nrhs_list in (("p3d64", (1,)), ("p3d80", (1, 16, 64))):
+            m2, nb2, desc2, sol2, _ = B.setup(wl)
+            dv2 = torch.tensor(m2[3], device="cuda")
+            ms2 = B.time_factor(sol2, dv2, max(args.steps, 3), 3)
+            ent = {"workload": desc2, "factor_ms": ms2, "factor_gflops": sol2.local.num_flops / ms2 / 1e6,
+                   "factor_frac_of_dmma_peak": sol2.local.num_flops / ms2 / 1e9 / peaks["dmma"], "solve": []}
+            for nr in nrhs_list:
+                rep, _ = B.solve_report(sol2, m2, nr, 5)
+                ent["solve"].append(rep)
+            extra[wl] = ent
+            del sol2, dv2
+            torch.cuda.empty_cache()
+        solver = None
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        fl, times, _, orc = cpu_reference_factor(mat, nb, cores, 2)
-        sec = min(times[1:]) if len(times) > 1 else times[0]
+        ref = CpuReference(mat, nb, cores)
+        last, fl, what = ref.sampled(2, 20.0)     # ~10-20 s of CPU work in two steps
+        sec = min(ref.run(last), ref.run(last))
         cpu = {"value": fl / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port", "seconds": sec,
-               "sample": "one full factorization of the same workload (after one warm-up run), OpenMP tasks on "
-                         "%d threads + sequential OpenBLAS 0.3.31 (restated reference OMP build)" % cores}
-        # the reference's solve (sequential tree sweeps, src/spllt_solve_mod.F90:244-411) on the same factor
-        try:
-            from spllt_b200 import matrices as M2
-            nr = args.nrhs
-            xs2 = np.asfortranarray(np.tile(np.arange(1.0, nr + 1), (n, 1)))
-            rhs2 = np.asfortranarray(M2.matvec(n, ptr, row, val, xs2))
-            orc.prepare_solve(nr)
-            ts = []
-            for _ in range(3):
-                xx = rhs2.copy(order="F")
-                t0 = time.perf_counter()
-                orc.solve(xx, 0)
-                ts.append(time.perf_counter() - t0)
-            cpu["solve_seconds_per_rhs"] = min(ts) / nr
-            cpu["solve_sample"] = "forward + backward solve of the same system, nrhs=%d, restated reference solve on 1 thread" % nr
-            if solve is not None:
-                solve["cpu_seconds_per_rhs"] = cpu["solve_seconds_per_rhs"]
-        except Exception as e:   # the baseline is a report, never a reason to lose the bench line
-            cpu["solve_seconds_per_rhs"] = None
-            cpu["solve_sample"] = "unavailable: %r" % (e,)
+               "sample": "%s (best of 2); OpenMP tasks on %d threads + sequential OpenBLAS 0.3.31 (restated "
+                         "reference OMP build)" % (what, cores)}
 
     if rank == 0:
         out = {
             "metric": "factor_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": solver.scaling(), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc + ", METIS nested dissection, nemin=32", "n": n, "nnz_lower": int(val.size),
-                       "nnz_L": int(s.num_factor), "flops_per_step": int(flops), "nb": nb,
-                       "multi_gpu": solver.describe(),
-                       "l2": "working set %.2f GB > 126 MB L2, no flush needed" %
-                             (L.spllt_b200_arena_doubles(s.akeep) * 8 / 1e9)},
+                       "flops_per_step": int(flops), "nb": nb,
+                       "l2": "working set (factor) far above the 126 MB L2, no flush needed"},
             "factor_seconds": ms / 1e3, "analyse_seconds_host": t_analyse,
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(solver.launches_per_factor() * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu, "solve": solve, "parity": parity,
+            "clocks": clk, "e2e": e2e, "gpu_launches": None,
+            "roofline": roofline, "roofline_solve": roofline_solve, "cpu_baseline": cpu, "solve": solve,
+            "parity": parity, "extra": extra,
         }
+        out["config"].update(cfg_more)
+        out["gpu_launches"] = launches_per_factor * args.steps
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

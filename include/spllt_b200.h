@@ -71,7 +71,8 @@ int spllt_b200_chkerr(int n, const int *ptr, const int *row, const double *val, 
 /* ---- counters for bench.py */
 long long spllt_b200_factor_launches(void *fkeep);  /* kernels per spllt_factor             */
 long long spllt_b200_solve_launches(void *fkeep, int job);
-double spllt_b200_tile_flops(void *akeep);          /* flops issued by the DMMA tile kernels */
+double spllt_b200_tile_flops(void *akeep);          /* flops issued by the DMMA tile kernels (padded tiles) */
+double spllt_b200_tile_flops_algo(void *akeep);     /* algorithmic flops of the same tiles: 2 K per entry i >= j */
 /* launch counts of one factorization: panel, tile_s, tile_l, total */
 void spllt_b200_launch_breakdown(void *akeep, long long *out4);
 

@@ -21,6 +21,51 @@ def build(force=False):
     return LIB
 
 
+SSI = os.path.join(HERE, "libssids_standin.so")
+_ssi = None
+
+
+def build_ssids():
+    srcs = [os.path.join(HERE, "ssids_standin.cpp"), os.path.join(HERE, "..", "spllt_b200", "csrc", "symbolic.cpp")]
+    if not os.path.exists(SSI) or any(os.path.exists(f) and os.path.getmtime(SSI) < os.path.getmtime(f) for f in srcs):
+        subprocess.check_call(["make", "-C", HERE, "-B", "libssids_standin.so"], stdout=subprocess.DEVNULL)
+    return SSI
+
+
+def symbolic(n, ptr, row, nemin=32, ordering=1):
+    """order, sptr, sparent, rptr, rlist (1-based, SSIDS conventions) from the SSIDS stand-in
+    (METIS nested dissection + supernodal symbolic factorization), without the product library."""
+    global _ssi
+    if _ssi is None:
+        build_ssids()
+        L = C.CDLL(SSI)
+        ip, llp = C.POINTER(C.c_int), C.POINTER(C.c_longlong)
+        L.ssi_analyse.argtypes = [C.c_int, ip, ip, C.c_int, C.c_int]
+        L.ssi_analyse.restype = C.c_void_p
+        L.ssi_nnodes.argtypes = [C.c_void_p]
+        L.ssi_rlist_len.argtypes = [C.c_void_p]
+        L.ssi_rlist_len.restype = C.c_longlong
+        L.ssi_get.argtypes = [C.c_void_p, ip, ip, ip, llp, ip]
+        L.ssi_free.argtypes = [C.c_void_p]
+        _ssi = L
+    L = _ssi
+    ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+    row = np.ascontiguousarray(row, dtype=np.int32)
+    h = L.ssi_analyse(n, _ip(ptr), _ip(row), nemin, ordering)
+    if not h:
+        raise RuntimeError("symbolic analysis failed")
+    nn = L.ssi_nnodes(h)
+    order = np.zeros(max(n, 1), np.int32)
+    sptr = np.zeros(nn + 1, np.int32)
+    sparent = np.zeros(max(nn, 1), np.int32)
+    rptr = np.zeros(nn + 1, np.int64)
+    rlist = np.zeros(max(L.ssi_rlist_len(h), 1), np.int32)
+    L.ssi_get(h, _ip(order), _ip(sptr), _ip(sparent), _llp(rptr), _ip(rlist))
+    ln = L.ssi_rlist_len(h)
+    L.ssi_free(h)
+    return order[:n], sptr, sparent[:nn], rptr, rlist[:ln]
+
+
 def _blas_path():
     import scipy
     c = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libscipy_openblas*.so"))
@@ -59,6 +104,7 @@ def lib():
         L.orc_get_lcol.argtypes = [vp, C.c_int, dp]
         L.orc_get_factor.argtypes = [vp, dp]
         L.orc_factor.argtypes = [vp, dp, C.c_int]
+        L.orc_factor_prefix.argtypes = [vp, dp, C.c_int, C.c_int]
         L.orc_prepare_solve.argtypes = [vp, C.c_int, C.c_int]
         L.orc_prepare_solve.restype = C.c_longlong
         L.orc_get_sblocks.argtypes = [vp, ip]
@@ -141,6 +187,11 @@ class Oracle:
     def factor(self, val, nthreads=1):
         v = np.ascontiguousarray(val, dtype=np.float64)
         self.L.orc_factor(self.h, _dp(v), nthreads)
+
+    def factor_prefix(self, val, nthreads, last_node):
+        """Bounded sample (bench.py's CPU arm): factorizes nodes 1..last_node only."""
+        v = np.ascontiguousarray(val, dtype=np.float64)
+        self.L.orc_factor_prefix(self.h, _dp(v), nthreads, int(last_node))
 
     def factor_entries(self):
         out = np.zeros(max(self.L.orc_factor_size(self.h), 1))

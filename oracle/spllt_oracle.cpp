@@ -1040,13 +1040,29 @@ static void subtree_factorize(Oracle& o, int root, const double* val, std::vecto
 // src/spllt_stf_mod.F90:18-192 (spllt_stf_factorize) + spllt_wait.  nthreads<=1: sequential
 // submission order; otherwise OpenMP tasks with the dependency contract of
 // src/spllt_factorization_task_mod.F90.
+// last_node < nnodes: BOUNDED SAMPLE for timing the CPU arm of bench.py -- only nodes
+// 1..last_node are initialised, factorized and applied (a prefix of the postorder is closed under
+// descendants, so every node in it sees exactly the updates it sees in the full factorization;
+// their updates into later ancestors are computed as usual, the ancestors stay unfactorized).
+// last_node must not cut a pruned subtree (small[last_node] >= 0).
+static void factor_prefix(void* h, const double* val, int nthreads, int last_node);
 extern "C" void orc_factor(void* h, const double* val, int nthreads) {
+  factor_prefix(h, val, nthreads, ((Oracle*)h)->nnodes);
+}
+extern "C" void orc_factor_prefix(void* h, const double* val, int nthreads, int last_node) {
+  Oracle& o = *(Oracle*)h;
+  factor_prefix(h, val, nthreads, std::max(0, std::min(last_node, o.nnodes)));
+}
+static void factor_prefix(void* h, const double* val, int nthreads, int last_node) {
   Oracle& o = *(Oracle*)h;
   if (o.n == 0) return;
   bool tasks = nthreads > 1;
   int nw = tasks ? nthreads : 1;
   // spllt_factorization_init  src/spllt_factorization_mod.F90:347-423
-  o.lcol.assign(o.nbcol + 1, {});
+  const bool sample = last_node < o.nnodes;
+  // sample mode: storage of the nodes beyond the sample (update targets only) is allocated once
+  // and left alone afterwards, so that a timed step costs what the sample costs
+  if (!sample || (int)o.lcol.size() != o.nbcol + 1) o.lcol.assign(o.nbcol + 1, {});
   std::vector<Work> ws(nw);
   for (Work& w : ws) {
     w.workspace.assign((size_t)o.maxmn * o.maxmn, 0.0);
@@ -1054,8 +1070,11 @@ extern "C" void orc_factor(void* h, const double* val, int nthreads) {
     w.col_list.assign(o.maxmn, 0);
     w.map.assign(o.n + 1, 0);
   }
-  for (int s = 1; s <= o.nnodes; ++s) activate_node(o, s);
-  for (int s = 1; s <= o.nnodes; ++s)
+  for (int s = 1; s <= o.nnodes; ++s) {
+    if (sample && s > last_node && !o.lcol[o.bc[o.nd(s).blk_sa].bcol].empty()) continue;
+    activate_node(o, s);
+  }
+  for (int s = 1; s <= last_node; ++s)
     if (o.small[s] == 1) {
       Node& rn = o.nd(s);
       i64 b = (i64)rn.index.size() - (rn.en - rn.sa + 1);
@@ -1063,7 +1082,7 @@ extern "C" void orc_factor(void* h, const double* val, int nthreads) {
     }
   auto body = [&]() {
     for (int s = 1; s <= o.nnodes; ++s) {
-      if (o.small[s] != 0) continue;
+      if (o.small[s] != 0 || s > last_node) continue;
       if (tasks) {
         // src/spllt_factorization_task_mod.F90:1333-1414: inout on every tile of the node
         Oracle* po = &o;
@@ -1073,7 +1092,7 @@ extern "C" void orc_factor(void* h, const double* val, int nthreads) {
         init_node(o, s, val);
     }
 #pragma omp taskwait
-    for (int s = 1; s <= o.nnodes; ++s) {
+    for (int s = 1; s <= last_node; ++s) {
       if (o.small[s] < 0) continue;
       if (o.small[s] == 1) {
         // spllt_subtree_factorize_apply  src/spllt_factorization_mod.F90:196-261

@@ -103,6 +103,7 @@ def load_library(path=None):
         "spllt_b200_factor_launches": (C.c_longlong, [vp]),
         "spllt_b200_solve_launches": (C.c_longlong, [vp, C.c_int]),
         "spllt_b200_tile_flops": (C.c_double, [vp]),
+        "spllt_b200_tile_flops_algo": (C.c_double, [vp]),
         "spllt_b200_launch_breakdown": (None, [vp, llp]),
         "spllt_b200_profile_factor": (None, [vp, vp, dp, C.c_char_p]),
         "spllt_b200_node_owner": (C.c_int, [vp, C.c_int]),

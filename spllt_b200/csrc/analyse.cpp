@@ -338,6 +338,19 @@ static i64 count_tiles(const Region& r, int T, int TN) {
   return c;
 }
 
+// Algorithmic flops of one tile task: 2 kk per destination entry (i, j) with i >= j inside the
+// mt x nt tile -- what the reference's dgemm / dsyrk calls on the same tile would count
+// (src/spllt_kernels_mod.F90:1261-1292, :2197-2213) -- independent of the padded T x TN extent
+// the kernel issues.
+double tile_algo_flops(const TileTask& t) {
+  double entries = 0;
+  for (int j = 0; j < t.nt; ++j) {
+    const int first = std::max(t.i0, t.j0 + j);          // first row with i >= j in this column
+    entries += std::max(0, t.i0 + t.mt - first);
+  }
+  return 2.0 * t.kk * entries;
+}
+
 // tiles of T rows x TN columns covering the lower part of the region
 static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r, int T, int TN) {
   const HNode& nd = *r.nd;
@@ -360,6 +373,7 @@ static void emit_tiles(Analysis& A, std::vector<TileTask>& dst, const Region& r,
       t.pad = r.excl;
       dst.push_back(t);
       A.tile_flops += 2.0 * T * TN * r.kk;
+      A.tile_flops_algo += tile_algo_flops(t);
     }
   }
 }
@@ -378,6 +392,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   A.tile_tasks.clear();
   A.launches.clear();
   A.tile_flops = 0;
+  A.tile_flops_algo = 0;
 
   // ---- inter-node update maps
   i64 nrows = 0;

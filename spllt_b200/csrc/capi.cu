@@ -9,9 +9,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "../../include/spllt_b200.h"
+#include "cuda_check.h"
 #include "engine.h"
 
 using namespace spllt;
@@ -55,6 +57,43 @@ Engine* EE(void* fkeep) { return fkeep ? &((FKeep*)fkeep)->eng : nullptr; }
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
+}
+
+// Runs `f`; a CUDA failure / missing device / host allocation failure inside it becomes the
+// reference's error code in info%flag (src/spllt_data_mod.F90:31-35) instead of leaving the C ABI
+// as an exception or aborting the caller's process.  Returns the flag (0 = no failure).
+template <class F>
+int guarded(spllt_inform_t* info, F&& f) {
+  int flag = SPLLT_SUCCESS, stat = 0;
+  try {
+    f();
+    return SPLLT_SUCCESS;
+  } catch (const CudaFailure& e) {
+    flag = e.oom() ? SPLLT_ERROR_ALLOCATION : SPLLT_ERROR_UNKNOWN;
+    stat = (int)e.err;
+  } catch (const NoDevice&) {
+    flag = SPLLT_ERROR_UNKNOWN;
+  } catch (const std::bad_alloc&) {
+    fprintf(stderr, "spllt_b200: host allocation failed\n");
+    flag = SPLLT_ERROR_ALLOCATION;
+  }
+  if (info) {
+    info->flag = flag;
+    info->stat = stat;
+  }
+  return flag;
+}
+
+// Pivot status of the last factorization once it has completed (the stream is idle): the
+// reference leaves info%flag of the asynchronous spllt_factor untouched; here the first call on
+// the handle after spllt_wait() reports SPLLT_ERROR_NOT_POS_DEF (-20).
+int post_flag(Engine* e) {
+  if (!e || !e->uploaded || !e->factored || !e->stream) return SPLLT_SUCCESS;
+  if (cudaStreamQuery(e->stream) != cudaSuccess) {
+    cudaGetLastError();
+    return SPLLT_SUCCESS;   // still running: unknown yet
+  }
+  return e->pivot_flag() ? SPLLT_ERROR_NOT_POS_DEF : SPLLT_SUCCESS;
 }
 
 void analyse_impl(void** akeep, void** fkeep, spllt_options_t* options, int n, const int* ptr, const int* row,
@@ -147,14 +186,15 @@ void solve_impl(void* fkeep, int nrhs, double* x, spllt_inform_t* info, int job,
     if (info) fill_info(*e->A, info, SPLLT_WARNING_PARAM_VALUE);
     return;
   }
-  e->solve_host(x, nrhs, job);
-  int flag = SPLLT_SUCCESS;
-  if (wait) {
-    e->sync();
-    if (job == 1) mirror_y(*e, nrhs);
-    if (e->pivot_flag()) flag = SPLLT_ERROR_NOT_POS_DEF;
-  }
-  if (info) fill_info(*e->A, info, flag);
+  if (info) fill_info(*e->A, info, SPLLT_SUCCESS);
+  guarded(info, [&] {
+    e->solve_host(x, nrhs, job);
+    if (wait) {
+      e->sync();
+      if (job == 1) mirror_y(*e, nrhs);
+      if (e->pivot_flag() && info) info->flag = SPLLT_ERROR_NOT_POS_DEF;
+    }
+  });
 }
 
 }  // namespace
@@ -164,12 +204,12 @@ extern "C" {
 
 void spllt_analyse(void** akeep, void** fkeep, spllt_options_t* options, int n, int* ptr, int* row,
                    spllt_inform_t* info, int* order) {
-  analyse_impl(akeep, fkeep, options, n, ptr, row, info, order, ORDER_METIS);
+  guarded(info, [&] { analyse_impl(akeep, fkeep, options, n, ptr, row, info, order, ORDER_METIS); });
 }
 
 void spllt_b200_analyse(void** akeep, void** fkeep, spllt_options_t* options, int n, const int* ptr, const int* row,
                         spllt_inform_t* info, int* order, int ordering) {
-  analyse_impl(akeep, fkeep, options, n, ptr, row, info, order, ordering);
+  guarded(info, [&] { analyse_impl(akeep, fkeep, options, n, ptr, row, info, order, ordering); });
 }
 
 void spllt_factor(void* akeep, void* fkeep, spllt_options_t* options, int nnz, double* val, spllt_inform_t* info) {
@@ -181,8 +221,11 @@ void spllt_factor(void* akeep, void* fkeep, spllt_options_t* options, int nnz, d
   if (!val) fprintf(stderr, "Error, val provided by the user is empty\n");
   if (!A || !e || !val) return;
   if ((i64)nnz != A->nnz) fprintf(stderr, "Warning, nnz = %d differs from ptr(n+1)-1 = %lld\n", nnz, (long long)A->nnz);
-  e->factor_host(val);
   fill_info(*A, info, SPLLT_SUCCESS);
+  // asynchronous like the reference: a pivot failure of THIS factorization is only known after
+  // spllt_wait(); it is reported (flag -20) by the first call on the handle after the wait, and
+  // spllt_b200_pivot_flag / spllt_b200_factor_status read it directly.
+  guarded(info, [&] { e->factor_host(val); });
 }
 
 void spllt_prepare_solve(void* akeep, void* fkeep, int nb, int nrhs, long* worksize, spllt_inform_t* info) {
@@ -202,6 +245,9 @@ void spllt_prepare_solve(void* akeep, void* fkeep, int nb, int nrhs, long* works
   e->prep_nrhs = nrhs;
   if (worksize) *worksize = worksize_of(*A, nrhs);
   fill_info(*A, info, flag);
+  guarded(info, [&] {
+    if (post_flag(e) && info) info->flag = SPLLT_ERROR_NOT_POS_DEF;
+  });
 }
 
 void spllt_set_mem_solve(void* akeep, void* fkeep, int nb, int nrhs, long worksize, double* y, double* workspace,
@@ -218,6 +264,9 @@ void spllt_set_mem_solve(void* akeep, void* fkeep, int nb, int nrhs, long worksi
   }
   e->host_y = y;
   fill_info(*A, info, SPLLT_SUCCESS);
+  guarded(info, [&] {
+    if (post_flag(e) && info) info->flag = SPLLT_ERROR_NOT_POS_DEF;
+  });
 }
 
 void spllt_solve_workspace_size(void* fkeep, int nworker, int nrhs, long* size) {
@@ -251,8 +300,10 @@ void spllt_wait(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     live = g_live;
   }
-  for (Engine* e : live)
-    if (e->uploaded) e->sync();
+  guarded(nullptr, [&] {
+    for (Engine* e : live)
+      if (e->uploaded) e->sync();
+  });
 }
 
 // src/utils_mod.F90:432-478 (host-side acceptance metric; prints like the reference)
@@ -459,7 +510,9 @@ long long spllt_b200_lcol_size(void* akeep, int bcol) {
   int r0 = A.bcol_c[bcol - 1] * A.nb;
   return (long long)(nd.m - r0) * std::min(A.nb, nd.n - r0);
 }
-void spllt_b200_get_lcol(void* fkeep, int bcol, double* out) { EE(fkeep)->get_lcol(bcol - 1, out); }
+void spllt_b200_get_lcol(void* fkeep, int bcol, double* out) {
+  guarded(nullptr, [&] { EE(fkeep)->get_lcol(bcol - 1, out); });
+}
 long long spllt_b200_factor_size(void* akeep) {
   const Analysis& A = *AA(akeep);
   long long s = 0;
@@ -469,23 +522,27 @@ long long spllt_b200_factor_size(void* akeep) {
 void spllt_b200_get_factor(void* fkeep, double* out) {
   Engine* e = EE(fkeep);
   const Analysis& A = *e->A;
-  i64 s = 0;
-  for (int g = 0; g < A.nbcol; ++g) {
-    const HNode& nd = A.nodes[A.bcol_node[g]];
-    int r0 = A.bcol_c[g] * A.nb;
-    e->get_lcol(g, out + s);
-    s += (i64)(nd.m - r0) * std::min(A.nb, nd.n - r0);
-  }
+  guarded(nullptr, [&] {
+    i64 s = 0;
+    for (int g = 0; g < A.nbcol; ++g) {
+      const HNode& nd = A.nodes[A.bcol_node[g]];
+      int r0 = A.bcol_c[g] * A.nb;
+      e->get_lcol(g, out + s);
+      s += (i64)(nd.m - r0) * std::min(A.nb, nd.n - r0);
+    }
+  });
 }
 
 void spllt_b200_set_stream(void* fkeep, void* stream) {
   Engine* e = EE(fkeep);
-  e->upload_tables();
-  e->stream = stream ? (cudaStream_t)stream : e->own;
+  guarded(nullptr, [&] {
+    e->upload_tables();
+    e->stream = stream ? (cudaStream_t)stream : e->own;
+  });
 }
 void spllt_b200_factor_dev(void* akeep, void* fkeep, const double* d_val, spllt_inform_t* info) {
-  EE(fkeep)->factor(d_val);
   if (info) fill_info(*AA(akeep), info, SPLLT_SUCCESS);
+  guarded(info, [&] { EE(fkeep)->factor(d_val); });
 }
 void spllt_b200_solve_dev(void* fkeep, int nrhs, double* d_x, int ldx, int job, spllt_inform_t* info) {
   Engine* e = EE(fkeep);
@@ -493,11 +550,17 @@ void spllt_b200_solve_dev(void* fkeep, int nrhs, double* d_x, int ldx, int job, 
     if (info) fill_info(*e->A, info, SPLLT_WARNING_PARAM_VALUE);
     return;
   }
-  e->solve(d_x, ldx, nrhs, job);
   if (info) fill_info(*e->A, info, SPLLT_SUCCESS);
+  guarded(info, [&] { e->solve(d_x, ldx, nrhs, job); });
 }
-void spllt_b200_get_fwd(void* fkeep, int nrhs, double* out) { EE(fkeep)->get_fwd(nrhs, out); }
-int spllt_b200_pivot_flag(void* fkeep) { return EE(fkeep)->pivot_flag(); }
+void spllt_b200_get_fwd(void* fkeep, int nrhs, double* out) {
+  guarded(nullptr, [&] { EE(fkeep)->get_fwd(nrhs, out); });
+}
+int spllt_b200_pivot_flag(void* fkeep) {
+  int v = 0;
+  int rc = guarded(nullptr, [&] { v = EE(fkeep)->pivot_flag(); });
+  return rc ? rc : v;
+}
 
 long long spllt_b200_factor_launches(void* fkeep) {
   const Analysis& A = *EE(fkeep)->A;
@@ -516,6 +579,7 @@ long long spllt_b200_solve_launches(void* fkeep, int job) {
   return tot;
 }
 double spllt_b200_tile_flops(void* akeep) { return AA(akeep)->tile_flops; }
+double spllt_b200_tile_flops_algo(void* akeep) { return AA(akeep)->tile_flops_algo; }
 void spllt_b200_launch_breakdown(void* akeep, long long* out4) {
   out4[0] = out4[1] = out4[2] = out4[3] = 0;
   for (const Launch& L : AA(akeep)->launches)
@@ -524,16 +588,16 @@ void spllt_b200_launch_breakdown(void* akeep, long long* out4) {
 }
 
 void spllt_b200_profile_factor(void* fkeep, const double* d_val, double* ms4, const char* csv) {
-  EE(fkeep)->profile_factor(d_val, ms4, csv);
+  guarded(nullptr, [&] { EE(fkeep)->profile_factor(d_val, ms4, csv); });
 }
 
 void spllt_b200_profile_solve(void* fkeep, int nrhs, double* d_x, int ldx, double* ms6, const char* csv) {
-  EE(fkeep)->profile_solve(d_x, ldx, nrhs, ms6, csv);
+  guarded(nullptr, [&] { EE(fkeep)->profile_solve(d_x, ldx, nrhs, ms6, csv); });
 }
 
 void spllt_b200_trace_solve(void* fkeep, int nrhs, double* d_x, int ldx, unsigned long long* out_f,
                             unsigned long long* out_b) {
-  EE(fkeep)->trace_solve(d_x, ldx, nrhs, out_f, out_b);
+  guarded(nullptr, [&] { EE(fkeep)->trace_solve(d_x, ldx, nrhs, out_f, out_b); });
 }
 // multi-GPU: the upper-tree lists (sizes2 = {forward tasks, backward tasks}); same record layout
 void spllt_b200_pipe_top_sizes(void* akeep, long long* sizes2) {
@@ -578,9 +642,13 @@ void spllt_b200_get_pipe(void* akeep, int* tasks_f, int* tasks_b, int* nodes, in
   for (int e : A.pexpect) *expect++ = e;
 }
 double spllt_b200_peak_probe(int kind, int iters, void* stream) {
-  require_gpu();
-  if (kind >= 10) return launch_dmma_warps(iters, kind - 10, (cudaStream_t)stream);
-  return kind == 0 ? launch_dmma_peak(iters, (cudaStream_t)stream) : launch_dfma_peak(iters, (cudaStream_t)stream);
+  double fl = 0;
+  guarded(nullptr, [&] {
+    require_gpu();
+    if (kind >= 10) fl = launch_dmma_warps(iters, kind - 10, (cudaStream_t)stream);
+    else fl = kind == 0 ? launch_dmma_peak(iters, (cudaStream_t)stream) : launch_dfma_peak(iters, (cudaStream_t)stream);
+  });
+  return fl;
 }
 
 void* spllt_b200_arena_ptr(void* fkeep) {

@@ -4,6 +4,8 @@
 // (src/spllt_stf_mod.F90:18-192, src/spllt_solve_mod.F90:244-411).
 #include "engine.h"
 
+#include "cuda_check.h"
+
 #include <cuda.h>
 
 #include <cstdio>
@@ -12,14 +14,6 @@
 
 namespace spllt {
 
-#define CK(x)                                                                                            \
-  do {                                                                                                   \
-    cudaError_t e_ = (x);                                                                                \
-    if (e_ != cudaSuccess) {                                                                             \
-      fprintf(stderr, "spllt_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
-      abort();                                                                                           \
-    }                                                                                                    \
-  } while (0)
 
 template <class T>
 static T* upload(const std::vector<T>& v) {
@@ -30,7 +24,7 @@ static T* upload(const std::vector<T>& v) {
   return d;
 }
 
-static bool g_kernels_ready = false;
+static unsigned long long g_kernels_ready = 0;   // bit d: kernel attributes set on device d
 
 void require_gpu() {
   int cnt = 0;
@@ -40,19 +34,19 @@ void require_gpu() {
             "spllt_b200: no CUDA device available -- the numerical phase has no CPU fallback "
             "(cudaGetDeviceCount: %s)\n",
             cudaGetErrorString(e));
-    abort();
+    throw NoDevice{};
   }
 }
 
 void Engine::upload_tables() {
   if (uploaded) return;
   require_gpu();
-  if (!g_kernels_ready) {
+  CK(cudaGetDevice(&device));
+  if (!(g_kernels_ready >> (device & 63) & 1ull)) {   // function attributes are per device
     kernels_init();
     pipe_init();
-    g_kernels_ready = true;
+    g_kernels_ready |= 1ull << (device & 63);
   }
-  CK(cudaGetDevice(&device));
   const Analysis& S = *A;
   if (!own_stream) {
     CK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
@@ -103,7 +97,7 @@ void Engine::upload_tables() {
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) {
       fprintf(stderr, "spllt_b200: cuTensorMapEncodeTiled not available\n");
-      abort();
+      throw CudaFailure{cudaErrorNotSupported, __FILE__, __LINE__};
     }
     encode_t encode = (encode_t)fn;
     std::vector<CUtensorMap> maps(std::max(S.nnodes, 1));
@@ -120,7 +114,7 @@ void Engine::upload_tables() {
         if (r != CUDA_SUCCESS) {
           fprintf(stderr, "spllt_b200: cuTensorMapEncodeTiled failed (%d) for node %d (m=%d ld=%d)\n", (int)r, k, nd.m,
                   nd.ld);
-          abort();
+          throw CudaFailure{cudaErrorInvalidValue, __FILE__, __LINE__};
         }
       }
       void** dst = pass == 0 ? &d_tmaps : &d_tmaps_b;
@@ -163,6 +157,9 @@ void Engine::upload_tables() {
 
 void Engine::ensure_solve_buffers(int nrhs) {
   if (nrhs <= xw_nrhs) return;
+  // the captured solve graphs point into the buffers that are about to be replaced
+  for (auto& e : solve_graphs) cudaGraphExecDestroy(e.second);
+  solve_graphs.clear();
   if (d_xw) CK(cudaFree(d_xw));
   if (d_x) CK(cudaFree(d_x));
   CK(cudaMalloc(&d_xw, std::max<i64>((i64)A->n * nrhs, 1) * sizeof(double)));
@@ -351,19 +348,22 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
   ms4[0] = ms;
   FILE* f = csv ? fopen(csv, "w") : nullptr;
-  if (f) fprintf(f, "launch,kind,tag,depth,ctas,ms,flops_issued\n");
+  if (f) fprintf(f, "launch,kind,tag,depth,ctas,ms,flops_issued,flops_algo\n");
   for (size_t i = 0; i < S.launches.size(); ++i) {
     const Launch& L = S.launches[i];
     CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]));
     if (L.kind == L_EXCHANGE) continue;
     ms4[1 + L.kind] += ms;
     if (f) {
-      double fl = 0;
+      double fl = 0, fa = 0;
       if (L.kind != L_PANEL) {
         double T = L.kind == L_TILE_L ? 128.0 : 64.0, TN = L.kind == L_TILE_L ? (double)S.tile_n : 64.0;
-        for (i64 k = L.begin; k < L.begin + L.count; ++k) fl += 2.0 * T * TN * S.tile_tasks[k].kk;
+        for (i64 k = L.begin; k < L.begin + L.count; ++k) {
+          fl += 2.0 * T * TN * S.tile_tasks[k].kk;
+          fa += tile_algo_flops(S.tile_tasks[k]);
+        }
       }
-      fprintf(f, "%zu,%d,%d,%d,%lld,%.6f,%.0f\n", i, L.kind, L.tag, L.depth, (long long)L.count, ms, fl);
+      fprintf(f, "%zu,%d,%d,%d,%lld,%.6f,%.0f,%.0f\n", i, L.kind, L.tag, L.depth, (long long)L.count, ms, fl, fa);
     }
   }
   if (f) fclose(f);
@@ -676,6 +676,14 @@ void Engine::release() {
   cudaFree(d_porder);
   if (d_xw) cudaFree(d_xw);
   if (d_x) cudaFree(d_x);
+  // nothing of the old analysis may survive: a later spllt_analyse on the same handles starts clean
+  d_xw = d_x = nullptr;
+  xw_nrhs = 0;
+  xm_doubles = psync_ints = 0;
+  dinv_valid = factored = false;
+  graph_val = nullptr;
+  graph_stream = nullptr;
+  host_y = nullptr;
   if (stream == own) stream = nullptr;
   if (own_stream) cudaStreamDestroy(own);
   own_stream = false;

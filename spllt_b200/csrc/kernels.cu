@@ -15,6 +15,8 @@
 
 #include "kernels.cuh"
 
+#include "cuda_check.h"
+
 namespace spllt {
 
 #define FULL 0xffffffffu
@@ -104,7 +106,7 @@ constexpr int PLD = IB + 1;   // X rows: conflict-free when thread r reads X[r][
 constexpr int LTD = IB + 2;   // Lt rows: even, so (c*LTD + j) is 16-byte aligned for even j
 constexpr int PB = 16;        // register block
 constexpr int PANEL_THREADS = 128 + TRSM_ROWS;
-constexpr int SMEM_PANEL = (IB * LTD + TRSM_ROWS * PLD + 2 * IB + IB + 8) * 8;
+constexpr int SMEM_PANEL = (IB * LTD + TRSM_ROWS * PLD + 2 * IB + IB + 8 + 2) * 8;
 
 template <bool DBG>
 __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ arena,
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
   double* col = X + TRSM_ROWS * PLD;      // [2][IB]
   double* dinv = col + 2 * IB;            // [IB]
   unsigned long long* blk_done = reinterpret_cast<unsigned long long*>(dinv + IB);  // [4]
+  int* store_flag = reinterpret_cast<int*>(blk_done + IB / PB);
   const PanelTask t = tasks[blockIdx.x];
   const int pw = t.pw, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* gd = arena + t.d_off;
@@ -136,11 +139,16 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
       for (int r = r2; r < pw; r += PANEL_THREADS / IB) Lt[cc * LTD + r] = (cc <= r) ? gd[(i64)r * t.ld + cc] : 0.0;
     }
   }
+  // Every read of the un-factorized block by this CTA is complete (its values sit in shared
+  // memory).  Each CTA of the panel draws a ticket; the one that draws the LAST ticket knows that
+  // every other CTA of the panel has read the original block too, so it is the one that stores
+  // L_pp in place.  No CTA ever waits for another one: no assumption on dispatch order.
+  // The ticket is only needed when the factorization is finished: its round trip to L2 is hidden.
   __syncthreads();
-  // every read of the un-factorized block by this CTA is complete: tell the storing CTA
-  if (tid == 0 && !t.store) {
+  int ticket = t.ngroup - 1;
+  if (tid == 0 && t.ngroup > 1) {
     __threadfence();
-    atomicAdd(pcount + t.group, 1);
+    ticket = atomicAdd(pcount + t.group, 1);
   }
   if (DBG && tid == 0) dbg[blockIdx.x * 8 + 1] = clock64();
 
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
               if (r >= k && r < pw) Lt[k * LTD + r] = me * s;
               if (r == k) {
                 dinv[k] = s;
-                if (t.store && !(akk > 0.0)) atomicMin(info, t.col0 + k + 1);
+                if (!(akk > 0.0)) atomicMin(info, t.col0 + k + 1);   // every CTA of the panel sees the same pivot
               }
             }
           }
@@ -202,16 +210,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
       if ((tid & 31) == 0) mbar_arrive(blk_done + c0 / PB);
     }
     if (DBG && tid == 0) dbg[blockIdx.x * 8 + 2] = clock64();
-    // store L_pp: only the CTA with the highest block index of the panel, and only once the
-    // other CTAs (all dispatched before this one) have read the original block
-    if (t.store) {
-      if (tid == 0 && t.ngroup > 1) {
-        volatile int* pc = pcount + t.group;
-        while (*pc < t.ngroup - 1) {
-        }
-        __threadfence();
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    // store L_pp: only the CTA that drew the panel's last ticket (see above)
+    if (tid == 0) *store_flag = ticket == t.ngroup - 1;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (*store_flag) {
       const int cc = tid & 63, r2 = tid >> 6;
       if (cc < pw) {
 #pragma unroll 8
@@ -1163,14 +1165,6 @@ constexpr int SMEM_TILE_S = 2 * (64 + 64) * SLD * 8;
 constexpr int SMEM_TILE_L = 3 * (128 + 128) * SLD * 8;
 constexpr int SMEM_SOLVE_MAX = 200 * 1024;
 
-#define CK(x)                                                                             \
-  do {                                                                                    \
-    cudaError_t e_ = (x);                                                                 \
-    if (e_ != cudaSuccess) {                                                              \
-      fprintf(stderr, "spllt_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
-      abort();                                                                            \
-    }                                                                                     \
-  } while (0)
 
 void kernels_init() {
   CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));

@@ -53,9 +53,9 @@ struct HNode {
 // every CTA factorizes the pw x pw diagonal block in shared memory (redundantly -- it is on
 // the critical path anyway and this saves a launch) and then solves its own chunk of rows,
 //   rows <- rows * L_pp^-T.
-// L_pp is stored in place by exactly one CTA of the panel, the one with the highest block
-// index (`store`), and only after every other CTA of the panel has reported (through the
-// panel's counter) that it has finished reading the un-factorized block.
+// L_pp is stored in place by exactly one CTA of the panel: every CTA draws a ticket from the
+// panel's counter once it has read the un-factorized block, and the CTA that draws the last
+// ticket stores (nobody waits for anybody).  `store` marks one task per panel for bookkeeping.
 struct PanelTask {
   i64 d_off;         // arena offset of the pw x pw diagonal block
   i64 r_off;         // first row of this chunk (below the diagonal block)
@@ -199,6 +199,7 @@ struct Analysis {
   std::vector<i64> q_rp;           //   rowpos[q_rp[j] + r] = row position of source row r in dest
   std::vector<int> rowpos;
   double tile_flops = 0;           // flops issued by the tile kernels (incl. masked halves)
+  double tile_flops_algo = 0;      // algorithmic flops of the same tiles (2 kk per entry with i >= j)
 
   // solve schedule (forward order; the backward sweep walks it in reverse)
   std::vector<SolveBcol> sbcols;
@@ -230,5 +231,6 @@ void partition_tree(Analysis& A, int rank, int world);
 void build_factor_schedule(Analysis& A, int tile_l_min);
 void build_solve_schedule(Analysis& A);
 void ref_blocks(const Analysis& A, std::vector<RefBlock>& out);
+double tile_algo_flops(const TileTask& t);
 
 }  // namespace spllt

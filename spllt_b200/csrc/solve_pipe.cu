@@ -45,16 +45,10 @@
 
 #include "kernels.cuh"
 
+#include "cuda_check.h"
+
 namespace spllt {
 
-#define CK(x)                                                                                            \
-  do {                                                                                                   \
-    cudaError_t e_ = (x);                                                                                \
-    if (e_ != cudaSuccess) {                                                                             \
-      fprintf(stderr, "spllt_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
-      abort();                                                                                           \
-    }                                                                                                    \
-  } while (0)
 
 namespace {
 
@@ -879,7 +873,7 @@ static int pipe_prepare() {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_solve_pipe<RC, FWD>, PT, pipe_smem(RC)));
   if (per < 1) {
     fprintf(stderr, "spllt_b200: pipelined solve kernel does not fit on an SM\n");
-    abort();
+    throw CudaFailure{cudaErrorLaunchOutOfResources, __FILE__, __LINE__};
   }
   return per * sms;
 }

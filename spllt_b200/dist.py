@@ -162,6 +162,14 @@ class DistSpLLT:
     def pivot_flag(self):
         return self.local.pivot_flag()
 
+    def profile_factor(self, d_val):
+        """per-kernel-kind milliseconds of one un-graphed factorization (this rank's launches)"""
+        return self.local.profile_factor(d_val.data_ptr())
+
+    def solve_path(self):
+        return ("multi-GPU: persistent pipelined kernels on the rank's subtrees, upper tree redundantly, "
+                "two NCCL all-reduces of the work vector")
+
     # -------------------------------------------------------------- reporting
     def work_multiplier(self):
         return 1   # one factorization is shared by all ranks (strong scaling)
