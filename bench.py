@@ -425,8 +425,8 @@ def main():
 
     # ---------------- roofline of the dominant kernel (DMMA tile updates)
     roofline = None
+    prof = solver.profile_factor(d_val)      # collective: every rank runs its un-graphed, event-timed pass
     if rank == 0:
-        prof = solver.profile_factor(d_val)
         bd = np.zeros(4, dtype=np.int64)
         L.spllt_b200_launch_breakdown(s.akeep, bd.ctypes.data_as(C.POINTER(C.c_longlong)))
         issued = float(L.spllt_b200_tile_flops(s.akeep))            # padded tiles, masked halves included

@@ -111,29 +111,48 @@ void spllt_b200_get_pipe(void *akeep, int *tasks_f, int *tasks_b, int *nodes, in
  * DMMA (kind 0) or DFMA (kind 1) loop on every SM; returns the flops it will execute */
 double spllt_b200_peak_probe(int kind, int iters, void *stream);
 
-/* ---- multi-GPU hooks (one process per GPU; collectives are done by the caller on arena
- * slices, e.g. torch.distributed over NCCL) */
+/* ---- multi-GPU (one process per GPU, all GPUs of one NVLink / NVSwitch box).
+ * Subtrees of the assembly tree are mapped to ranks by proportional mapping; the upper tree is
+ * distributed by block column (owner computes) and walked in the same step order on every rank.
+ * Every rank maps every peer's factor arena (CUDA IPC): a subtree's contributions into the upper
+ * tree are scattered straight into the owning rank's HBM by the update kernel's epilogue
+ * (RED.ADD.F64 on peer addresses -- spllt_subtree_apply_buffer / spllt_scatter_block of the
+ * reference, src/spllt_factorization_mod.F90:39-191, without the generated-element buffer), and a
+ * finished upper-tree block column is copied into the peers' arenas by its owner's SMs and
+ * announced by a flag.  Usage on every rank r of `world`:
+ *   spllt_analyse(...);  spllt_b200_partition(akeep, fkeep, r, world);
+ *   spllt_b200_comm_export(fkeep, mine);   all-gather the 128-byte records (MPI / torch.distributed);
+ *   spllt_b200_comm_attach(fkeep, r, world, table);
+ *   spllt_factor / spllt_b200_factor_dev, spllt_wait -- as on one GPU, called by every rank. */
 void *spllt_b200_arena_ptr(void *fkeep);            /* device pointer of the HBM arena        */
-/* node ownership: rank r factorizes the subtrees given to it by proportional mapping; nodes
- * above the split are "shared" (owner -1) and factorized by every rank after the reduction */
 void spllt_b200_partition(void *akeep, void *fkeep, int rank, int world);
-int spllt_b200_node_owner(void *akeep, int node);  /* node 1-based; -1 = shared top */
+int spllt_b200_node_owner(void *akeep, int node);  /* node 1-based; -1 = upper tree (distributed by block column) */
 /* host-only partition (no device state): used by the CPU multi-process tests */
 void spllt_b200_partition_host(void *akeep, int rank, int world);
+#define SPLLT_B200_HANDLE_BYTES 128
+int spllt_b200_comm_export(void *fkeep, void *out128);                       /* 0 = ok */
+int spllt_b200_comm_attach(void *fkeep, int rank, int world, const void *all_handles);
 /* out[node] = number of inner panels (64 columns) this rank's schedule holds for each node */
 void spllt_b200_panel_coverage(void *akeep, long long *out);
-/* [begin, end) offsets (doubles) of the shared top-of-tree region in the arena */
-void spllt_b200_shared_region(void *akeep, long long *begin, long long *end);
-/* distributed upper tree: launch records (8 columns: kind depth begin count phase tag stream
- * deadline; kind 3 = exchange point: begin = node (0-based), count = block column, tag = owner),
- * ranges of them run by the caller, block-column pack / unpack around its broadcasts */
+/* this rank's launch records (8 columns: kind depth begin count phase tag stream deadline; kind 0
+ * panel, 1 / 2 tile updates, 3 push of global block column `begin` to the peers, 4 wait for it; phase 1 =
+ * upper tree, depth = step index there) and tile tasks (10 columns: node i0 j0 k0 mt nt kk src off ld) */
 long long spllt_b200_num_launch_records(void *akeep);
 void spllt_b200_get_launch_records(void *akeep, long long *out);
-void spllt_b200_run_launches(void *fkeep, long long first, long long last);
-void spllt_b200_bcol_region(void *akeep, int node, int c, long long *off, int *ld, int *rows, int *cols);
-void spllt_b200_pack_bcol(void *akeep, void *fkeep, int node, int c, double *d_buf);
-void spllt_b200_unpack_bcol(void *akeep, void *fkeep, int node, int c, const double *d_buf);
+long long spllt_b200_num_tile_tasks(void *akeep);
+void spllt_b200_get_tile_tasks(void *akeep, long long *out);
+/* upper-tree steps, identical on every rank (4 columns: node (0-based), local block column, owner, slot) */
+int spllt_b200_num_top_steps(void *akeep);
+void spllt_b200_get_top_steps(void *akeep, int *out);
+void spllt_b200_get_bcol_owner(void *akeep, int *out);   /* [nbcol] */
 int spllt_b200_dist_top(void *akeep);
+/* `world` ranks emulated on ONE GPU inside one process (engines partitioned with rank 0..world-1):
+ * the same per-rank programs, kernels and peer addressing, enqueued in an order in which no kernel
+ * waits for a later one.  For tests on single-GPU machines.  Synchronises. */
+int spllt_b200_emulate_ranks_factor(void **fkeeps, int world, const double *d_val);
+/* {max |a - b|, max |b|} over the lower trapezoids of the nodes rank A holds: two factorizations of
+ * the same matrix with the same ordering on the same device (distributed vs single-GPU) */
+int spllt_b200_compare_factor(void *akeep_a, void *fkeep_a, void *akeep_b, void *fkeep_b, double *out2);
 /* multi-GPU solve, one call per phase (all asynchronous on the stream).  The caller sums the work
  * vector (spllt_b200_xw_ptr: n x nrhs doubles, row-major) over the ranks after phases 1 and 4.
  * 0: permute the rhs in, drop the entries this rank does not own; 1: forward sweep of the rank's
@@ -141,8 +160,6 @@ int spllt_b200_dist_top(void *akeep);
  * sweep of the rank's subtrees, drop foreign entries; 5: permute the solution out (d_x, ldx). */
 void spllt_b200_solve_phase(void *fkeep, int nrhs, double *d_x, int ldx, int phase);
 void *spllt_b200_xw_ptr(void *fkeep, int nrhs);
-/* phase 0 = assemble + local subtrees, phase 1 = shared top; both asynchronous */
-void spllt_b200_factor_phase(void *akeep, void *fkeep, const double *d_val, int phase);
 
 #ifdef __cplusplus
 }

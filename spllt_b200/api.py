@@ -122,17 +122,20 @@ def load_library(path=None):
         "spllt_b200_partition": (None, [vp, vp, C.c_int, C.c_int]),
         "spllt_b200_partition_host": (None, [vp, C.c_int, C.c_int]),
         "spllt_b200_panel_coverage": (None, [vp, llp]),
-        "spllt_b200_shared_region": (None, [vp, llp, llp]),
         "spllt_b200_num_launch_records": (C.c_longlong, [vp]),
         "spllt_b200_get_launch_records": (None, [vp, llp]),
-        "spllt_b200_run_launches": (None, [vp, C.c_longlong, C.c_longlong]),
-        "spllt_b200_bcol_region": (None, [vp, C.c_int, C.c_int, llp, ip, ip, ip]),
-        "spllt_b200_pack_bcol": (None, [vp, vp, C.c_int, C.c_int, vp]),
-        "spllt_b200_unpack_bcol": (None, [vp, vp, C.c_int, C.c_int, vp]),
+        "spllt_b200_num_tile_tasks": (C.c_longlong, [vp]),
+        "spllt_b200_get_tile_tasks": (None, [vp, llp]),
+        "spllt_b200_num_top_steps": (C.c_int, [vp]),
+        "spllt_b200_get_top_steps": (None, [vp, ip]),
+        "spllt_b200_get_bcol_owner": (None, [vp, ip]),
+        "spllt_b200_comm_export": (C.c_int, [vp, vp]),
+        "spllt_b200_comm_attach": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+        "spllt_b200_emulate_ranks_factor": (C.c_int, [vpp, C.c_int, vp]),
+        "spllt_b200_compare_factor": (C.c_int, [vp, vp, vp, vp, dp]),
         "spllt_b200_dist_top": (C.c_int, [vp]),
         "spllt_b200_solve_phase": (None, [vp, C.c_int, vp, C.c_int, C.c_int]),
         "spllt_b200_xw_ptr": (vp, [vp, C.c_int]),
-        "spllt_b200_factor_phase": (None, [vp, vp, vp, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)  # AttributeError = the library does not export a declared symbol

@@ -215,6 +215,11 @@ int build_analysis(int n, const int* ptr, const int* row, int nb, int nemin, int
     }
   }
   A.arena = off;
+  A.own_begin = 0;
+  A.own_end = off;
+  A.bcol_owner.assign(A.nbcol, 0);
+  A.bcol_step.assign(A.nbcol, -1);
+  A.top_steps.clear();
 
   // block column -> node table
   A.bcol_node.resize(A.nbcol);
@@ -488,12 +493,32 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   std::vector<int> nsteps(nn, 0);
   for (int s = 0; s < nn; ++s)
     for (int c = 0; c < A.nodes[s].nc; ++c) nsteps[s] += cdiv(std::min(nb, A.nodes[s].n - c * nb), IB);
-  for (int phase = 0; phase < 2; ++phase) {
+  auto emit_panel = [&](const HNode& nd, int k0, int pw) {
+    PanelTask pt;
+    pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
+    pt.ld = nd.ld;
+    pt.pw = pw;
+    pt.col0 = nd.sa + k0;
+    pt.pad = 0;
+    int r = k0 + pw;
+    size_t g0 = A.panel_tasks.size();
+    pt.group = A.npanel_groups++;
+    do {
+      pt.r_off = nd.off + (i64)r * nd.ld + k0;
+      pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
+      pt.store = 0;
+      A.panel_tasks.push_back(pt);
+      r += TRSM_ROWS;
+    } while (r < nd.m);
+    A.panel_tasks.back().store = 1;
+    for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
+  };
+
+  // ---- phase 0: every node on one GPU; the subtrees this rank owns on several
+  {
+    const int phase = 0;
     cur_phase = phase;
-    auto mine = [&](int s) {
-      int own = A.nodes[s].owner;
-      return (A.world <= 1) ? (phase == 0) : (phase == 0 ? own == A.rank : own < 0);
-    };
+    auto mine = [&](int s) { return A.world <= 1 || A.nodes[s].owner == A.rank; };
     std::vector<int> t0(nn, 0);
     int nslots = 0;
     for (int s = 0; s < nn; ++s) {
@@ -509,7 +534,8 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     // Exclusive (atomic-free) launches: implemented and parity-tested, but measured SLOWER than
     // RED.ADD.F64 (the read-modify-write needs two dependent global round trips per row block,
     // the RED is fire-and-forget): 64^3 tile time 16.3 -> 24.8 ms.  Opt-in only.
-    const bool excl_ok = (A.nb % 2 == 0) && !getenv("SPLLT_B200_NO_TMA") && getenv("SPLLT_B200_EXCL") && !defer;
+    const bool excl_ok = (A.nb % 2 == 0) && !getenv("SPLLT_B200_NO_TMA") && getenv("SPLLT_B200_EXCL") && !defer &&
+                         A.world <= 1;
     const i64 excl_min = getenv("SPLLT_B200_EXCL_MIN") ? atoll(getenv("SPLLT_B200_EXCL_MIN")) : 148;
     for (int s = 0; s < nn; ++s) {
       if (!mine(s)) continue;
@@ -519,14 +545,6 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         for (int p = 0; p * IB < w; ++p) at[t++].push_back({s, c, p});
       }
     }
-    // Distributed upper tree (multi-GPU, phase 1): every rank walks the same slots but only
-    // factorizes the block columns it owns and only computes the updates whose destination
-    // block column it owns; a finished block column is broadcast by its owner (L_EXCHANGE)
-    // before anybody uses it as a source.  No reductions are needed.
-    const bool dtop = phase == 1 && A.world > 1 && A.dist_top;
-    auto bowner = [&](int node, int c) { return A.bcol_owner[A.nodes[node].bcol0 + c]; };
-    std::vector<Region> regions_post;
-    std::vector<std::pair<int, int>> exchanges;
     for (int d = 0; d < nslots; ++d) {
       if (at[d].empty()) continue;
       i64 p0 = A.panel_tasks.size();
@@ -537,56 +555,17 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         int pw = std::min(IB, w - st.p * IB);
         int k0 = r0 + st.p * IB;
         const bool last_in_bcol = k0 + pw >= r0 + w;
-        const bool own_bc = !dtop || bowner(st.node, st.c) == A.rank;
-        if (own_bc) {
-          PanelTask pt;
-          pt.d_off = nd.off + (i64)k0 * nd.ld + k0;
-          pt.ld = nd.ld;
-          pt.pw = pw;
-          pt.col0 = nd.sa + k0;
-          pt.pad = 0;
-          int r = k0 + pw;
-          size_t g0 = A.panel_tasks.size();
-          pt.group = A.npanel_groups++;
-          do {
-            pt.r_off = nd.off + (i64)r * nd.ld + k0;
-            pt.nrows = std::max(0, std::min(TRSM_ROWS, nd.m - r));
-            pt.store = 0;
-            A.panel_tasks.push_back(pt);
-            r += TRSM_ROWS;
-          } while (r < nd.m);
-          A.panel_tasks.back().store = 1;
-          for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
-          // a3 inside the block column: the columns right of this panel (K = pw)
-          if (!last_in_bcol) add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
-        }
-        if (last_in_bcol && dtop) {
-          exchanges.push_back({st.node, st.c});
-          // a3: later block columns of the node that this rank owns
-          for (int c2 = st.c + 1; c2 < nd.nc; ++c2)
-            if (bowner(st.node, c2) == A.rank)
-              regions_post.push_back({&nd, c2 * nb, std::min((c2 + 1) * nb, nd.n), 0, nd.m, r0, w, -1});
-          // a4: destination (ancestor, block column) runs that this rank owns
-          if (st.c + 1 == nd.nc && nd.m > nd.n) {
-            const int* idx = A.index.data() + nd.idx_off;
-            int r = nd.n;
-            while (r < nd.m) {
-              int a = A.col2node[idx[r]];
-              int cb = (idx[r] - A.nodes[a].sa) / nb;
-              int cend = std::min(A.nodes[a].sa + (cb + 1) * nb - 1, A.nodes[a].en);
-              int r1 = r;
-              while (r1 < nd.m && idx[r1] <= cend) ++r1;
-              if (bowner(a, cb) == A.rank) regions_post.push_back({&nd, r, r1, 0, nd.m, 0, nd.n, st.node});
-              r = r1;
-            }
-          }
-        } else if (last_in_bcol) {
+        emit_panel(nd, k0, pw);
+        // a3 inside the block column: the columns right of this panel (K = pw)
+        if (!last_in_bcol) add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+        if (last_in_bcol) {
           // a3: the finished block column updates the node's later block columns (K = w)
           if (st.c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
           // a4: the finished node updates its ancestors (K = n).  Only the columns that belong
           // to an ancestor whose first panel runs in the very next slot are on the critical path;
           // the rest is deferred to the background stream with the slot of the first ancestor
-          // that needs it as its deadline.
+          // that needs it as its deadline.  (Multi-GPU: ancestors in the upper tree live in their
+          // owner's arena -- the scatter goes there through the peer-mapped q_base addresses.)
           if (st.c + 1 == nd.nc && nd.m > nd.n) {
             const int* idx = A.index.data() + nd.idx_off;
             int r = nd.n, split = nd.n, dl = 1 << 30;
@@ -595,7 +574,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
               int a = A.col2node[idx[r]];
               int r1 = r;
               while (r1 < nd.m && idx[r1] <= A.nodes[a].en) ++r1;
-              int need = mine(a) ? t0[a] : (1 << 30);   // other phase: after the exchange step
+              int need = mine(a) ? t0[a] : (1 << 30);   // upper tree: after the barrier
               if (first && need <= d + 1) split = r1;   // urgent: the parent starts in the next slot
               else dl = std::min(dl, need);
               first = false;
@@ -618,14 +597,6 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
       if ((i64)A.panel_tasks.size() > p0)
         A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0, 0, 0});
       flush_tiles(d, 4);
-      if (dtop) {
-        for (auto& e : exchanges)
-          A.launches.push_back({L_EXCHANGE, d, (i64)e.first, (i64)e.second, phase, bowner(e.first, e.second), 0, 0});
-        exchanges.clear();
-        regions.insert(regions.end(), regions_post.begin(), regions_post.end());
-        regions_post.clear();
-        flush_tiles(d, 7);
-      }
       for (const Region& r : excl_regions) {   // one launch per big finishing node, after the shared ones
         emit_tiles(A, tl, r, 128, A.tile_n);
         std::stable_sort(tl.begin(), tl.end(), [](const TileTask& a, const TileTask& b) {
@@ -642,16 +613,89 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
       }
     }
   }
+
+  // ---- phase 1 (multi-GPU): the upper tree, one STEP per block column in the global order of
+  // A.top_steps.  Owner computes: the owner of a step's block column factorizes it (panel chain)
+  // and pushes it into every peer's arena; every rank applies it to the destination block columns
+  // IT owns -- later block columns of the node, and, when the node is complete, block columns of
+  // its ancestors.  Updates are split by urgency (static look-ahead): destinations whose own step
+  // comes within the next `window` steps are updated right away, the rest one step later, i.e.
+  // while the owner of the next step is busy with its panel chain.  Per rank everything is ONE
+  // in-order sequence, so a destination's chain always follows every update into it.
+  if (A.world > 1 && A.dist_top) {
+    cur_phase = 1;
+    const int window = std::max(1, getenv("SPLLT_B200_TOP_WINDOW") ? atoi(getenv("SPLLT_B200_TOP_WINDOW")) : 2);
+    std::vector<Region> rest;   // deferred updates of the previous step
+    auto flush_rest = [&](int t) {
+      if (rest.empty()) return;
+      regions.insert(regions.end(), rest.begin(), rest.end());
+      rest.clear();
+      flush_tiles(t, 5);
+    };
+    for (int t = 0; t < (int)A.top_steps.size(); ++t) {
+      const TopStep& ts_ = A.top_steps[t];
+      const HNode& nd = A.nodes[ts_.node];
+      const int g = nd.bcol0 + ts_.c;
+      const int r0 = ts_.c * nb, w = std::min(nb, nd.n - r0);
+      const bool own = ts_.owner == A.rank;
+      if (own) {
+        for (int k0 = r0; k0 < r0 + w; k0 += IB) {
+          const int pw = std::min(IB, r0 + w - k0);
+          i64 p0 = A.panel_tasks.size();
+          emit_panel(nd, k0, pw);
+          A.launches.push_back({L_PANEL, t, p0, (i64)A.panel_tasks.size() - p0, 1, 0, 0, 0});
+          if (k0 + pw < r0 + w) {
+            add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+            flush_tiles(t, 4);
+          }
+        }
+        A.launches.push_back({L_PUSH, t, (i64)g, 1, 1, 8, 0, 0});
+      } else {
+        flush_rest(t);
+        A.launches.push_back({L_WAIT, t, (i64)g, 1, 1, 9, 0, 0});
+      }
+      // updates from this block column (later block columns of the node) / this node (ancestors)
+      std::vector<Region> later;
+      for (int c2 = ts_.c + 1; c2 < nd.nc; ++c2) {
+        const int g2 = nd.bcol0 + c2;
+        if (A.bcol_owner[g2] != A.rank) continue;
+        Region rg{&nd, c2 * nb, std::min((c2 + 1) * nb, nd.n), 0, nd.m, r0, w, -1};
+        (A.bcol_step[g2] <= t + window ? regions : later).push_back(rg);
+      }
+      if (ts_.c + 1 == nd.nc && nd.m > nd.n) {
+        const int* idx = A.index.data() + nd.idx_off;
+        int r = nd.n;
+        while (r < nd.m) {
+          const int a = A.col2node[idx[r]];
+          const int cb = (idx[r] - A.nodes[a].sa) / nb;
+          const int cend = std::min(A.nodes[a].sa + (cb + 1) * nb - 1, A.nodes[a].en);
+          int r1 = r;
+          while (r1 < nd.m && idx[r1] <= cend) ++r1;
+          const int g2 = A.nodes[a].bcol0 + cb;
+          if (A.bcol_owner[g2] == A.rank) {
+            Region rg{&nd, r, r1, 0, nd.m, 0, nd.n, ts_.node};
+            (A.bcol_step[g2] <= t + window ? regions : later).push_back(rg);
+          }
+          r = r1;
+        }
+      }
+      flush_tiles(t, 7);
+      if (own) flush_rest(t);
+      rest.insert(rest.end(), later.begin(), later.end());
+    }
+    flush_rest((int)A.top_steps.size());
+  }
 }
 
 // Subtree -> GPU mapping (proportional mapping).  Starting from the roots, the heaviest
 // candidate subtree is repeatedly split -- its root joins the shared upper tree, its children
 // become candidates -- until the subtrees can be dealt to the ranks (largest first onto the
-// least loaded rank) within 10 % of perfect balance.  The upper tree is shared: every rank
-// receives its assembled entries through one sum all-reduce.  (The reference's pruning,
-// src/spllt_analyse_mod.F90:806-987, plays this role for CPU workers but aims at many small
+// least loaded rank) within 10 % of perfect balance.  The upper tree is distributed by block
+// column (see below); contributions of a subtree into it are scattered straight into the owning
+// rank's arena over NVLink (peer-mapped q_base addresses) -- the generated element of
+// src/spllt_factorization_mod.F90:224-237 never exists as a buffer.  (The reference's pruning,
+// src/spllt_analyse_mod.F90:806-987, plays the mapping role for CPU workers but aims at many small
 // subtrees: with nth = 8 it leaves 81 % of the flops of a 64^3 Poisson problem in the upper tree.)
-// The arena is re-laid out so that the shared nodes form one contiguous slice at its end.
 void partition_tree(Analysis& A, int rank, int world) {
   A.rank = rank;
   A.world = world;
@@ -688,27 +732,62 @@ void partition_tree(Analysis& A, int rank, int world) {
     for (size_t k = 0; k < cand.size(); ++k)
       for (int q = A.nodes[cand[k]].least_desc; q <= cand[k]; ++q) A.nodes[q].owner = where[k];
   }
-  // block-column ownership: subtrees follow their node; upper-tree block columns are dealt
-  // cyclically (owner computes: panels, and every update whose DESTINATION it is)
-  A.dist_top = (world > 1 && !getenv("SPLLT_B200_REPLICATED_TOP")) ? 1 : 0;
+  // ---- upper tree in STEPS: one per block column, ordered by the as-soon-as-possible slot of its
+  // first panel (the critical-path order of the tree), ties by node.  Block columns are dealt to
+  // the ranks cyclically in that order: consecutive steps -- in particular consecutive block
+  // columns of one node -- have different owners, so the panel chain of step t+1 overlaps the
+  // updates the other ranks still apply from step t.
+  A.dist_top = (world > 1) ? 1 : 0;
+  A.top_steps.clear();
+  A.bcol_step.assign(A.nbcol, -1);
   A.bcol_owner.assign(A.nbcol, 0);
-  {
-    int next = 0;
-    for (int s = 0; s < nn; ++s)
-      for (int c = 0; c < A.nodes[s].nc; ++c)
-        A.bcol_owner[A.nodes[s].bcol0 + c] = (A.nodes[s].owner >= 0 || world <= 1) ? std::max(A.nodes[s].owner, 0) : (next++ % world);
+  for (int s = 0; s < nn; ++s)
+    for (int c = 0; c < A.nodes[s].nc; ++c) A.bcol_owner[A.nodes[s].bcol0 + c] = std::max(A.nodes[s].owner, 0);
+  if (world > 1) {
+    std::vector<int> t0(nn, 0);
+    for (int s = 0; s < nn; ++s) {
+      if (A.nodes[s].owner >= 0) continue;
+      const HNode& nd = A.nodes[s];
+      int t = t0[s];
+      for (int c = 0; c < nd.nc; ++c) {
+        A.top_steps.push_back({s, c, 0, t});
+        t += cdiv(std::min(A.nb, nd.n - c * A.nb), IB);
+      }
+      if (nd.parent >= 0) t0[nd.parent] = std::max(t0[nd.parent], t);
+    }
+    std::stable_sort(A.top_steps.begin(), A.top_steps.end(),
+                     [](const TopStep& a, const TopStep& b) { return a.slot < b.slot; });
+    for (size_t t = 0; t < A.top_steps.size(); ++t) {
+      TopStep& st = A.top_steps[t];
+      st.owner = (int)(t % world);
+      const int g = A.nodes[st.node].bcol0 + st.c;
+      A.bcol_owner[g] = st.owner;
+      A.bcol_step[g] = (int)t;
+    }
   }
-  // arena layout: owned subtrees first, shared nodes last
+  // ---- arena layout, IDENTICAL on every rank (an arena offset names the same entry of L on every
+  // GPU, so a peer address is peer_base + offset): the subtrees of rank 0, of rank 1, ..., then
+  // the upper tree.  Every rank allocates the whole arena (7.8 GB for Poisson 100^3; HBM is 180 GB)
+  // but only ever touches its own subtrees and the upper tree.
   i64 off = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1) A.top_begin = off;
+  A.own_begin = A.own_end = 0;
+  const int npass = world > 1 ? world + 1 : 2;
+  for (int pass = 0; pass < npass; ++pass) {
+    const bool top_pass = pass == npass - 1;
+    if (top_pass) A.top_begin = off;
+    if (world > 1 && pass == rank) A.own_begin = off;
     for (int s = 0; s < nn; ++s) {
       HNode& nd = A.nodes[s];
-      bool shared = (world > 1) ? nd.owner < 0 : nd.small == 0;
-      if (shared != (pass == 1)) continue;
+      const bool take = world > 1 ? (top_pass ? nd.owner < 0 : nd.owner == pass) : ((nd.small == 0) == top_pass);
+      if (!take) continue;
       nd.off = off;
       off += rup((i64)nd.m * nd.ld, 16);
     }
+    if (world > 1 && pass == rank) A.own_end = off;
+  }
+  if (world <= 1) {
+    A.own_begin = 0;
+    A.own_end = off;
   }
   A.arena = off;
 }

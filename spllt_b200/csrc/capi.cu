@@ -653,12 +653,12 @@ double spllt_b200_peak_probe(int kind, int iters, void* stream) {
 
 void* spllt_b200_arena_ptr(void* fkeep) {
   Engine* e = EE(fkeep);
-  e->upload_tables();
-  return e->arena;
-}
-void spllt_b200_shared_region(void* akeep, long long* begin, long long* end) {
-  *begin = AA(akeep)->top_begin;
-  *end = AA(akeep)->arena;
+  void* p = nullptr;
+  guarded(nullptr, [&] {
+    e->upload_tables();
+    p = e->arena;
+  });
+  return p;
 }
 void spllt_b200_partition(void* akeep, void* fkeep, int rank, int world) {
   Analysis* A = AA(akeep);
@@ -683,8 +683,6 @@ void spllt_b200_panel_coverage(void* akeep, long long* out) {
   for (const PanelTask& t : A.panel_tasks)
     if (t.store) out[A.col2node[t.col0]]++;
 }
-// ---- multi-GPU stepping (distributed upper tree): the caller walks the launch records of
-// phase 1, runs the kernel ranges itself and performs the block-column broadcasts in between.
 long long spllt_b200_num_launch_records(void* akeep) { return (long long)AA(akeep)->launches.size(); }
 // 8 columns per record: kind depth begin count phase tag stream deadline
 void spllt_b200_get_launch_records(void* akeep, long long* out) {
@@ -696,34 +694,123 @@ void spllt_b200_get_launch_records(void* akeep, long long* out) {
     r[7] = L.deadline;
   }
 }
-void spllt_b200_run_launches(void* fkeep, long long first, long long last) {
-  Engine* e = EE(fkeep);
-  e->upload_tables();
-  e->dinv_valid = false;
-  for (long long i = first; i < last; ++i) e->launch_one(e->A->launches[i], e->stream, false);
-}
-// block column c (0-based) of node (1-based): arena offset, leading dimension, rows, columns
-void spllt_b200_bcol_region(void* akeep, int node, int c, long long* off, int* ld, int* rows, int* cols) {
+// tile tasks (10 columns): node i0 j0 k0 mt nt kk src off ld -- for host-side replays of the schedule
+long long spllt_b200_num_tile_tasks(void* akeep) { return (long long)AA(akeep)->tile_tasks.size(); }
+void spllt_b200_get_tile_tasks(void* akeep, long long* out) {
   const Analysis& A = *AA(akeep);
-  const HNode& nd = A.nodes[node - 1];
-  int r0 = c * A.nb;
-  *off = nd.off + (i64)r0 * nd.ld + r0;
-  *ld = nd.ld;
-  *rows = nd.m - r0;
-  *cols = std::min(A.nb, nd.n - r0);
+  for (size_t i = 0; i < A.tile_tasks.size(); ++i) {
+    const TileTask& t = A.tile_tasks[i];
+    long long* r = out + 10 * i;
+    r[0] = t.node; r[1] = t.i0; r[2] = t.j0; r[3] = t.k0; r[4] = t.mt; r[5] = t.nt; r[6] = t.kk; r[7] = t.src;
+    r[8] = t.off; r[9] = t.ld;
+  }
 }
-void spllt_b200_pack_bcol(void* akeep, void* fkeep, int node, int c, double* d_buf) {
-  long long off; int ld, rows, cols;
-  spllt_b200_bcol_region(akeep, node, c, &off, &ld, &rows, &cols);
-  Engine* e = EE(fkeep);
-  launch_pack(e->arena + off, ld, rows, cols, d_buf, e->stream);
+// upper-tree steps (multi-GPU), 4 columns: node (0-based), local block column, owner rank, slot
+int spllt_b200_num_top_steps(void* akeep) { return (int)AA(akeep)->top_steps.size(); }
+void spllt_b200_get_top_steps(void* akeep, int* out) {
+  const Analysis& A = *AA(akeep);
+  for (size_t t = 0; t < A.top_steps.size(); ++t) {
+    out[4 * t] = A.top_steps[t].node; out[4 * t + 1] = A.top_steps[t].c;
+    out[4 * t + 2] = A.top_steps[t].owner; out[4 * t + 3] = A.top_steps[t].slot;
+  }
 }
-void spllt_b200_unpack_bcol(void* akeep, void* fkeep, int node, int c, const double* d_buf) {
-  long long off; int ld, rows, cols;
-  spllt_b200_bcol_region(akeep, node, c, &off, &ld, &rows, &cols);
-  Engine* e = EE(fkeep);
-  e->dinv_valid = false;
-  launch_unpack(e->arena + off, ld, rows, cols, d_buf, e->stream);
+void spllt_b200_get_bcol_owner(void* akeep, int* out) {
+  const Analysis& A = *AA(akeep);
+  for (int g = 0; g < A.nbcol; ++g) out[g] = A.bcol_owner[g];
+}
+
+// ---- multi-GPU bootstrap (one process per GPU).  After spllt_b200_partition on every rank:
+//   spllt_b200_comm_export  -> 128 bytes (CUDA IPC handles of the rank's arena and flag block);
+//   all-gather them over the ranks (torch.distributed, MPI, a file -- the library does not care);
+//   spllt_b200_comm_attach  <- the table of world x 128 bytes: maps the peers' memory.
+// From then on spllt_factor / spllt_b200_factor_dev run the distributed factorization: every
+// rank calls them, exactly as on one GPU.
+int spllt_b200_comm_export(void* fkeep, void* out128) {
+  return guarded(nullptr, [&] { EE(fkeep)->export_handles(out128); });
+}
+int spllt_b200_comm_attach(void* fkeep, int rank, int world, const void* all_handles) {
+  return guarded(nullptr, [&] { EE(fkeep)->attach_peers(rank, world, all_handles, nullptr); });
+}
+
+// Several ranks EMULATED on one GPU inside one process (tests on a single-GPU box; the engines
+// were partitioned with rank = 0 .. world-1 of `world`): the per-rank programs are enqueued on one
+// stream, interleaved step by step in an order in which every flag is already raised when its
+// waiter starts (owner's chain + push first, then everybody's updates), barriers split into
+// arrive / wait rounds.  Same kernels, same peer addressing, no kernel ever waits for a later one.
+int spllt_b200_emulate_ranks_factor(void** fkeeps, int world, const double* d_val) {
+  return guarded(nullptr, [&] {
+    std::vector<Engine*> E(world);
+    std::vector<void*> table(2 * world);
+    for (int r = 0; r < world; ++r) {
+      E[r] = EE(fkeeps[r]);
+      E[r]->upload_tables();
+      table[2 * r] = E[r]->arena;
+      table[2 * r + 1] = E[r]->d_flags;
+    }
+    cudaStream_t st = E[0]->stream;
+    for (int r = 0; r < world; ++r)
+      if (!E[r]->comm_ready) E[r]->attach_peers(r, world, nullptr, table.data());
+    for (int r = 0; r < world; ++r) {
+      E[r]->ev_used = 0;
+      E[r]->factor_begin(d_val, st);
+      E[r]->factor_barrier(1, 1, st);
+    }
+    for (int r = 0; r < world; ++r) {
+      E[r]->factor_barrier(1, 2, st);
+      E[r]->enqueue_range(0, E[r]->phase0_end, st);
+      E[r]->factor_barrier(2, 1, st);
+    }
+    for (int r = 0; r < world; ++r) E[r]->factor_barrier(2, 2, st);
+    const Analysis& A0 = *E[0]->A;
+    for (size_t t = 0; t < A0.top_steps.size(); ++t) {
+      const int o = A0.top_steps[t].owner;
+      E[o]->enqueue_range(E[o]->step_ranges[t].begin, E[o]->step_ranges[t].after_push, st);
+      for (int r = 0; r < world; ++r)
+        E[r]->enqueue_range(r == o ? E[r]->step_ranges[t].after_push : E[r]->step_ranges[t].begin,
+                            E[r]->step_ranges[t].end, st);
+    }
+    for (int r = 0; r < world; ++r) {
+      E[r]->factor_end(st);
+      E[r]->factored = true;
+      E[r]->dinv_valid = true;
+    }
+    CK(cudaStreamSynchronize(st));
+  });
+}
+
+// max |a - b| / max |b| over the lower trapezoids of the nodes rank A holds (its subtrees + the
+// upper tree; every node on one GPU), A and B being two factorizations of the same matrix with the
+// same ordering on the same device (e.g. distributed vs single-GPU).  out2 = {max abs diff, max |b|}
+int spllt_b200_compare_factor(void* akeep_a, void* fkeep_a, void* akeep_b, void* fkeep_b, double* out2) {
+  return guarded(nullptr, [&] {
+    const Analysis &A = *AA(akeep_a), &B = *AA(akeep_b);
+    Engine *ea = EE(fkeep_a), *eb = EE(fkeep_b);
+    struct CmpNode { i64 off_a, off_b; int m, n, ld, pad; };
+    std::vector<CmpNode> v;
+    for (int k = 0; k < A.nnodes && k < B.nnodes; ++k) {
+      const HNode &a = A.nodes[k], &b = B.nodes[k];
+      if (A.world > 1 && a.owner >= 0 && a.owner != A.rank) continue;
+      if (a.m != b.m || a.n != b.n || a.ld != b.ld) {
+        out2[0] = out2[1] = -1.0;   // different analyses
+        return;
+      }
+      v.push_back({a.off, b.off, a.m, a.n, a.ld, 0});
+    }
+    ea->sync();
+    eb->sync();
+    CmpNode* d = nullptr;
+    unsigned long long* o = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(CmpNode)));
+    CK(cudaMalloc(&o, 16));
+    CK(cudaMemcpy(d, v.data(), v.size() * sizeof(CmpNode), cudaMemcpyHostToDevice));
+    CK(cudaMemset(o, 0, 16));
+    launch_compare_nodes(d, (int)v.size(), ea->arena, eb->arena, o, nullptr);
+    unsigned long long h[2];
+    CK(cudaMemcpy(h, o, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(o);
+    memcpy(out2, h, 16);
+  });
 }
 int spllt_b200_dist_top(void* akeep) { return AA(akeep)->dist_top; }
 void spllt_b200_solve_phase(void* fkeep, int nrhs, double* d_x, int ldx, int phase) {
@@ -734,14 +821,6 @@ void* spllt_b200_xw_ptr(void* fkeep, int nrhs) {
   e->upload_tables();
   e->ensure_solve_buffers(nrhs);
   return e->d_xw;
-}
-
-void spllt_b200_factor_phase(void* akeep, void* fkeep, const double* d_val, int phase) {
-  (void)akeep;
-  Engine* e = EE(fkeep);
-  e->upload_tables();
-  e->dinv_valid = false;   // the caller completes the factor; inverses are recomputed before the next solve
-  e->enqueue_factor(d_val, e->stream, phase);
 }
 
 }  // extern "C"

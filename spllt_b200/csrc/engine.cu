@@ -64,21 +64,38 @@ void Engine::upload_tables() {
   overlap_tiles = !getenv("SPLLT_B200_NO_OVERLAP");
   CK(cudaMalloc(&arena, std::max<i64>(S.arena, 1) * sizeof(double)));
   CK(cudaMemset(arena, 0, std::max<i64>(S.arena, 1) * sizeof(double)));
-  // A -> L map with arena addresses
+  CK(cudaMalloc(&d_flags, (F_BCOL + std::max(S.nbcol, 1)) * sizeof(int)));
+  CK(cudaMemset(d_flags, 0, (F_BCOL + std::max(S.nbcol, 1)) * sizeof(int)));
+  CK(cudaMalloc(&d_pushcnt, std::max(S.nbcol, 1) * sizeof(int)));
+  if (S.world <= 1) {   // single GPU: the "peer set" is this arena
+    peers = PeerSet{};
+    peers.rank = 0;
+    peers.world = 1;
+    peers.arena[0] = arena;
+    peers.flags[0] = d_flags;
+    comm_ready = true;
+  }
+  // A -> L map with arena addresses.  Multi-GPU: a rank assembles the entries of the block columns
+  // it owns (its subtrees, and its share of the upper tree).
   {
-    std::vector<i64> dst(S.nnz);
+    std::vector<i64> dst, src;
+    dst.reserve(S.nnz);
+    src.reserve(S.nnz);
     for (int g = 0; g < S.nbcol; ++g) {
+      if (S.world > 1 && S.bcol_owner[g] != S.rank) continue;
       const HNode& nd = S.nodes[S.bcol_node[g]];
-      for (i64 e = S.lmap_ptr[g]; e < S.lmap_ptr[g + 1]; ++e)
-        dst[e] = nd.off + (i64)S.lmap_row[e] * nd.ld + S.lmap_col[e];
+      for (i64 e = S.lmap_ptr[g]; e < S.lmap_ptr[g + 1]; ++e) {
+        dst.push_back(nd.off + (i64)S.lmap_row[e] * nd.ld + S.lmap_col[e]);
+        src.push_back(S.lmap_src[e]);
+      }
     }
+    lmap_count = (i64)dst.size();
     d_lmap_dst = upload(dst);
-    d_lmap_src = upload(S.lmap_src);
+    d_lmap_src = upload(src);
   }
   CK(cudaMalloc(&d_val, std::max<i64>(S.nnz, 1) * sizeof(double)));
   d_panel = upload(S.panel_tasks);
   d_tile = upload(S.tile_tasks);
-  d_qbase = upload(S.q_base);
   d_qld = upload(S.q_ld);
   d_qrp = upload(S.q_rp);
   d_rowpos = upload(S.rowpos);
@@ -152,7 +169,95 @@ void Engine::upload_tables() {
   int maxw = 1;
   for (const SolveBcol& b : S.sbcols) maxw = std::max(maxw, b.w);
   set_solve_maxw(maxw);
+  // launch index ranges: phase 0, then the upper-tree steps (multi-GPU)
+  phase0_end = 0;
+  while (phase0_end < (i64)S.launches.size() && S.launches[phase0_end].phase == 0) ++phase0_end;
+  step_ranges.assign(S.top_steps.size(), StepRange{0, 0, 0});
+  {
+    i64 i = phase0_end;
+    for (size_t t = 0; t < S.top_steps.size(); ++t) {
+      StepRange& r = step_ranges[t];
+      r.begin = r.after_push = i;
+      while (i < (i64)S.launches.size() && S.launches[i].depth == (int)t) {
+        if (S.launches[i].kind == L_PUSH) r.after_push = i + 1;
+        ++i;
+      }
+      r.end = i;
+    }
+  }
   uploaded = true;
+  if (comm_ready) upload_maps();
+}
+
+// q_base as ABSOLUTE addresses: destination column of every below-diagonal row, in the arena of the
+// rank that owns the destination block column (own arena, or a peer's mapping)
+void Engine::upload_maps() {
+  if (maps_ready) return;
+  const Analysis& S = *A;
+  std::vector<i64> qa(S.q_base.size());
+  const int nb = S.nb;
+  for (int k = 0; k < S.nnodes; ++k) {
+    const HNode& nd = S.nodes[k];
+    const int* idx = S.index.data() + nd.idx_off;
+    for (int r = nd.n; r < nd.m; ++r) {
+      const i64 g = nd.row_base + (r - nd.n);
+      int owner = 0;
+      if (S.world > 1) {
+        const int a = S.col2node[idx[r]];
+        owner = S.bcol_owner[S.nodes[a].bcol0 + (idx[r] - S.nodes[a].sa) / nb];
+      }
+      qa[g] = (i64)(uintptr_t)(peers.arena[owner] + S.q_base[g]);
+    }
+  }
+  if (d_qbase) cudaFree(d_qbase);
+  d_qbase = upload(qa);
+  maps_ready = true;
+}
+
+// ---- multi-GPU bootstrap.  export_handles: CUDA IPC handles of this rank's arena and flag block;
+// the caller gathers them from all ranks (torch.distributed / MPI all-gather of 128 bytes per rank)
+// and passes the table to attach_peers.  same_process (optional): raw device pointers instead --
+// {arena, flags} per rank -- for several ranks emulated inside one process on one GPU.
+void Engine::export_handles(void* out128) {
+  upload_tables();
+  cudaIpcMemHandle_t h[2];
+  CK(cudaIpcGetMemHandle(&h[0], arena));
+  CK(cudaIpcGetMemHandle(&h[1], d_flags));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(out128, h, 128);
+}
+
+void Engine::attach_peers(int rank, int world, const void* all_handles, void* const* same_process) {
+  upload_tables();
+  if (world > MAX_RANKS) {
+    fprintf(stderr, "spllt_b200: at most %d ranks\n", MAX_RANKS);
+    throw CudaFailure{cudaErrorInvalidValue, __FILE__, __LINE__};
+  }
+  peers = PeerSet{};
+  peers.rank = rank;
+  peers.world = world;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      peers.arena[p] = arena;
+      peers.flags[p] = d_flags;
+    } else if (same_process) {
+      peers.arena[p] = (double*)same_process[2 * p];
+      peers.flags[p] = (int*)same_process[2 * p + 1];
+    } else {
+      cudaIpcMemHandle_t h[2];
+      memcpy(h, (const char*)all_handles + 128 * (size_t)p, 128);
+      void *pa = nullptr, *pf = nullptr;
+      CK(cudaIpcOpenMemHandle(&pa, h[0], cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle(&pf, h[1], cudaIpcMemLazyEnablePeerAccess));
+      ipc_open.push_back(pa);
+      ipc_open.push_back(pf);
+      peers.arena[p] = (double*)pa;
+      peers.flags[p] = (int*)pf;
+    }
+  }
+  comm_ready = true;
+  maps_ready = false;
+  upload_maps();
 }
 
 void Engine::ensure_solve_buffers(int nrhs) {
@@ -178,7 +283,14 @@ void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
   DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
   switch (L.kind) {
     case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, d_counters + A->launches.size(), st); break;
-    case L_EXCHANGE: break;   // not a kernel: driven by the multi-GPU caller (spllt_b200/dist.py)
+    case L_PUSH: {
+      const HNode& nd = A->nodes[A->bcol_node[L.begin]];
+      const int r0 = A->bcol_c[L.begin] * A->nb;
+      launch_push_bcol(peers, nd.off + (i64)r0 * nd.ld + r0, nd.ld, nd.m - r0, std::min(A->nb, nd.n - r0), (int)L.begin,
+                       d_pushcnt, st);
+      break;
+    }
+    case L_WAIT: launch_wait_bcol(d_flags, (int)L.begin, st); break;
     case L_TILE_S: launch_tiles(d_tile + L.begin, L.count, false, arena, mp, st); break;
     case L_TILE_L:
       if (use_tma && background && A->tile_n == 64)
@@ -193,19 +305,36 @@ void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
   }
 }
 
-// Enqueue one factorization: zero L, scatter A, then every launch of the level schedule.
-// phase: -1 = everything; 0 = assemble + the subtrees this rank owns; 1 = shared top of the tree.
-void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
+// One factorization = prologue (epoch, zero L, scatter A), the launches of phase 0 (everything on
+// one GPU; this rank's subtrees on several), and -- multi-GPU -- the upper-tree steps between two
+// barriers over the ranks: after the first every rank has zeroed the block columns it accumulates,
+// so peers may scatter into them; after the second every contribution of a subtree has landed.
+void Engine::factor_begin(const double* dval, cudaStream_t st) {
   const Analysis& S = *A;
-  if (phase <= 0) {
+  launch_epoch_inc(d_flags, st);
+  if (S.world > 1) {
+    if (S.own_end > S.own_begin) CK(cudaMemsetAsync(arena + S.own_begin, 0, (S.own_end - S.own_begin) * sizeof(double), st));
+    if (S.arena > S.top_begin) CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
+    CK(cudaMemsetAsync(d_pushcnt, 0, std::max(S.nbcol, 1) * sizeof(int), st));
+  } else {
     CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
-    CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
-    CK(cudaMemsetAsync(d_counters, 0, (S.launches.size() + S.npanel_groups + 1) * sizeof(int), st));
-    launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
-    // several ranks add their contributions to the shared top: only rank 0 keeps A's entries there
-    if (S.world > 1 && S.rank != 0 && S.arena > S.top_begin)
-      CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
   }
+  CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
+  CK(cudaMemsetAsync(d_counters, 0, (S.launches.size() + S.npanel_groups + 1) * sizeof(int), st));
+  launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, lmap_count, st);
+}
+
+void Engine::factor_barrier(int id, int what, cudaStream_t st) {
+  if (A->world > 1) launch_rank_barrier(peers, id, what, st);
+}
+
+void Engine::factor_end(cudaStream_t st) {
+  launch_invert_diag(d_pnodes, d_strip_node, A->nstrips, arena, d_dinv, st);
+}
+
+// Launches [first, last) of the schedule.
+void Engine::enqueue_range(i64 first, i64 last, cudaStream_t st) {
+  const Analysis& S = *A;
   // Streams (all of it is captured into one CUDA graph):
   //   st   : panel launch of every slot + the updates on the critical path;
   //   side : the small-tile launch of a slot, forked so that it overlaps the large-tile one
@@ -219,7 +348,6 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     cudaEvent_t ev;
   };
   std::vector<Pending> pending;
-  size_t ev_used = 0;
   auto next_event = [&]() {
     if (ev_used == ev_pool.size()) {
       cudaEvent_t e;
@@ -229,18 +357,17 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     return ev_pool[ev_used++];
   };
   auto join_bg = [&](int slot) {   // wait for every background launch whose deadline is <= slot
-    int last = -1;
+    int lastp = -1;
     for (size_t k = 0; k < pending.size(); ++k)
-      if (pending[k].deadline <= slot) last = (int)k;
-    if (last < 0) return;
-    CK(cudaStreamWaitEvent(st, pending[last].ev, 0));   // bg is in-order: covers the earlier ones
-    pending.erase(pending.begin(), pending.begin() + last + 1);
+      if (pending[k].deadline <= slot) lastp = (int)k;
+    if (lastp < 0) return;
+    CK(cudaStreamWaitEvent(st, pending[lastp].ev, 0));   // bg is in-order: covers the earlier ones
+    pending.erase(pending.begin(), pending.begin() + lastp + 1);
   };
   cudaEvent_t ev_panel = nullptr;
-  for (size_t i = 0; i < S.launches.size(); ++i) {
+  for (i64 i = first; i < last; ++i) {
     const Launch& L = S.launches[i];
-    if (phase >= 0 && L.phase != phase) continue;
-    if (L.stream == 1 && fork) {
+    if (L.stream == 1 && fork && ev_panel) {
       CK(cudaStreamWaitEvent(bg, ev_panel, 0));
       launch_one(L, bg, true);
       cudaEvent_t e = next_event();
@@ -251,14 +378,15 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     if (L.kind == L_PANEL) {
       join_bg(L.depth);
       launch_one(L, st, false);
-      if (fork) {
+      if (fork && L.phase == 0) {
         ev_panel = next_event();
         CK(cudaEventRecord(ev_panel, st));
       }
       continue;
     }
-    if (fork && L.kind == L_TILE_S && i + 1 < S.launches.size() && S.launches[i + 1].kind == L_TILE_L &&
-        S.launches[i + 1].depth == L.depth && S.launches[i + 1].phase == L.phase && S.launches[i + 1].stream == 0) {
+    if (fork && L.kind == L_TILE_S && i + 1 < last && S.launches[i + 1].kind == L_TILE_L &&
+        S.launches[i + 1].depth == L.depth && S.launches[i + 1].phase == L.phase && S.launches[i + 1].stream == 0 &&
+        S.launches[i + 1].tag == L.tag) {
       CK(cudaEventRecord(ev_fork, st));
       CK(cudaStreamWaitEvent(side, ev_fork, 0));
       launch_one(L, side, false);
@@ -271,8 +399,21 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st, int phase) {
     launch_one(L, st, false);
   }
   join_bg(1 << 30);
-  // last launch of a complete factorization: inverses of the diagonal blocks for the solve phase
-  if (phase < 0) launch_invert_diag(d_pnodes, d_strip_node, S.nstrips, arena, d_dinv, st);
+}
+
+void Engine::enqueue_factor(const double* dval, cudaStream_t st) {
+  const Analysis& S = *A;
+  if (!comm_ready) {
+    fprintf(stderr, "spllt_b200: %d ranks but the peers are not attached (spllt_b200_comm_attach)\n", S.world);
+    throw CudaFailure{cudaErrorNotReady, __FILE__, __LINE__};
+  }
+  ev_used = 0;
+  factor_begin(dval, st);
+  factor_barrier(1, 0, st);
+  enqueue_range(0, phase0_end, st);
+  factor_barrier(2, 0, st);
+  enqueue_range(phase0_end, (i64)S.launches.size(), st);
+  factor_end(st);
 }
 
 void Engine::factor(const double* dval) {
@@ -286,7 +427,7 @@ void Engine::factor(const double* dval) {
     }
     cudaGraph_t g;
     CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_factor(dval, stream, -1);
+    enqueue_factor(dval, stream);
     CK(cudaStreamEndCapture(stream, &g));
     CK(cudaGraphInstantiate(&factor_graph, g, 0));
     CK(cudaGraphDestroy(g));
@@ -296,13 +437,14 @@ void Engine::factor(const double* dval) {
   if (use_graph)
     CK(cudaGraphLaunch(factor_graph, stream));
   else
-    enqueue_factor(dval, stream, -1);
+    enqueue_factor(dval, stream);
   factored = true;
   dinv_valid = true;   // enqueue_factor(phase -1) ends with launch_invert_diag
 }
 
 // Un-graphed factorization with one event pair per launch: milliseconds per kernel kind
-// (assemble+memset, panel, tile_s, tile_l) and, optionally, one CSV line per launch.
+// (assemble+memset, panel, tile_s, tile_l) and, optionally, one CSV line per launch.  Multi-GPU:
+// collective -- every rank must call it; pushes / waits / barriers are executed but not attributed.
 void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   upload_tables();
   dinv_valid = false;
@@ -313,17 +455,19 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   for (auto& e : ev) CK(cudaEventCreate(&e));
   cudaStream_t st = stream;
   CK(cudaEventRecord(ev[0], st));
-  CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
-  CK(cudaMemsetAsync(d_info, 0x7f, sizeof(int), st));
-  CK(cudaMemsetAsync(d_counters, 0, (S.launches.size() + S.npanel_groups + 1) * sizeof(int), st));
-  launch_assemble(arena, d_lmap_dst, d_lmap_src, dval, S.nnz, st);
+  factor_begin(dval, st);
   CK(cudaEventRecord(ev[1], st));
+  factor_barrier(1, 0, st);
   long long* dbg = nullptr;
   const char* dbg_env = getenv("SPLLT_B200_PANEL_DBG");
   int dbg_launch = dbg_env ? atoi(dbg_env) : -1;
   i64 dbg_count = 0;
+  std::vector<cudaEvent_t> ev0(S.launches.size());   // start of every launch (barriers / waits excluded)
+  for (auto& e : ev0) CK(cudaEventCreate(&e));
   for (size_t i = 0; i < S.launches.size(); ++i) {
     const Launch& L = S.launches[i];
+    if ((i64)i == phase0_end) factor_barrier(2, 0, st);
+    CK(cudaEventRecord(ev0[i], st));
     if ((int)i == dbg_launch && L.kind == L_PANEL) {
       dbg_count = L.count;
       CK(cudaMalloc(&dbg, dbg_count * 8 * sizeof(long long)));
@@ -333,6 +477,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
     }
     CK(cudaEventRecord(ev[i + 2], st));
   }
+  if (phase0_end == (i64)S.launches.size()) factor_barrier(2, 0, st);
   CK(cudaStreamSynchronize(st));
   if (dbg) {
     std::vector<long long> h(dbg_count * 8);
@@ -351,12 +496,11 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   if (f) fprintf(f, "launch,kind,tag,depth,ctas,ms,flops_issued,flops_algo\n");
   for (size_t i = 0; i < S.launches.size(); ++i) {
     const Launch& L = S.launches[i];
-    CK(cudaEventElapsedTime(&ms, ev[i + 1], ev[i + 2]));
-    if (L.kind == L_EXCHANGE) continue;
-    ms4[1 + L.kind] += ms;
+    CK(cudaEventElapsedTime(&ms, ev0[i], ev[i + 2]));
+    if (L.kind <= L_TILE_L) ms4[1 + L.kind] += ms;
     if (f) {
       double fl = 0, fa = 0;
-      if (L.kind != L_PANEL) {
+      if (L.kind == L_TILE_S || L.kind == L_TILE_L) {
         double T = L.kind == L_TILE_L ? 128.0 : 64.0, TN = L.kind == L_TILE_L ? (double)S.tile_n : 64.0;
         for (i64 k = L.begin; k < L.begin + L.count; ++k) {
           fl += 2.0 * T * TN * S.tile_tasks[k].kk;
@@ -368,6 +512,7 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   }
   if (f) fclose(f);
   for (auto& e : ev) CK(cudaEventDestroy(e));
+  for (auto& e : ev0) CK(cudaEventDestroy(e));
   factored = true;
 }
 
@@ -646,12 +791,20 @@ void Engine::release() {
   cudaFree(d_val);
   cudaFree(d_panel);
   cudaFree(d_tile);
-  cudaFree(d_qbase);
+  if (d_qbase) cudaFree(d_qbase);
   cudaFree(d_qld);
   cudaFree(d_qrp);
   cudaFree(d_rowpos);
   cudaFree(d_info);
   cudaFree(d_counters);
+  for (void* p : ipc_open) cudaIpcCloseMemHandle(p);
+  ipc_open.clear();
+  cudaFree(d_flags);
+  cudaFree(d_pushcnt);
+  d_flags = d_pushcnt = nullptr;
+  d_qbase = nullptr;
+  comm_ready = maps_ready = false;
+  peers = PeerSet{};
   if (d_tmaps) cudaFree(d_tmaps);
   if (d_tmaps_b) cudaFree(d_tmaps_b);
   d_tmaps = d_tmaps_b = nullptr;

@@ -32,6 +32,8 @@ struct Engine {
   cudaStream_t side = nullptr;  // second stream: small-tile launches overlap the large-tile launch of their slot
   cudaStream_t bg = nullptr;    // low-priority stream: deferred inter-node updates
   std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  i64 lmap_count = 0;             // A -> L entries this rank assembles
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_tiles = true;
   int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
@@ -75,6 +77,25 @@ struct Engine {
   double* d_x = nullptr;   // staging copy of the caller's host x
   int xw_nrhs = 0;
 
+  // ---- multi-GPU (one rank per GPU): peer-mapped arenas / flag blocks, see kernels.cuh PeerSet
+  PeerSet peers{};
+  bool comm_ready = false;        // world == 1, or attach_peers() has run
+  bool maps_ready = false;        // q_base (absolute addresses) uploaded
+  int* d_flags = nullptr;         // this rank's flag block (F_EPOCH / F_BAR / F_BCOL)
+  int* d_pushcnt = nullptr;       // [nbcol] CTAs of a push that have finished (zeroed per factorization)
+  std::vector<void*> ipc_open;    // mappings to close on release
+  struct StepRange { i64 begin, after_push, end; };
+  std::vector<StepRange> step_ranges;   // launch index ranges of the upper-tree steps
+  i64 phase0_end = 0;                   // launches [0, phase0_end) belong to phase 0
+
+  void export_handles(void* out128);                       // arena + flag IPC handles (2 x 64 bytes)
+  void attach_peers(int rank, int world, const void* all_handles, void* const* same_process);
+  void upload_maps();
+  void factor_begin(const double* dval, cudaStream_t st);  // epoch, zero, assemble
+  void factor_barrier(int id, int what, cudaStream_t st);
+  void enqueue_range(i64 first, i64 last, cudaStream_t st);
+  void factor_end(cudaStream_t st);                         // inverses of the diagonal blocks
+
   cudaGraphExec_t factor_graph = nullptr;
   const double* graph_val = nullptr;
   cudaStream_t graph_stream = nullptr;
@@ -86,7 +107,7 @@ struct Engine {
 
   void upload_tables();
   void ensure_solve_buffers(int nrhs);
-  void enqueue_factor(const double* dval, cudaStream_t st, int phase);
+  void enqueue_factor(const double* dval, cudaStream_t st);
   void factor(const double* dval);
   void factor_host(const double* val);
   void profile_factor(const double* dval, double* ms5, const char* csv);

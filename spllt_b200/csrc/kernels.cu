@@ -428,7 +428,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
       for (int j = 0; j < FN; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
-          if (rp[j][e] >= 0) atomicAdd(arena + qb[j][e] + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+          if (rp[j][e] >= 0) atomicAdd(reinterpret_cast<double*>(qb[j][e]) + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
     }
   }
 }
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
             for (int e = 0; e < 2; ++e) {
               int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
               bool ok = ii < t.mt && jj < t.nt && gi >= gj;
-              dst[j][e] = ok ? arena + qb[j][e] + (i64)mp.rowpos[qr[j][e] + gi] * ql[j][e] : nullptr;
+              dst[j][e] = ok ? reinterpret_cast<double*>(qb[j][e]) + (i64)mp.rowpos[qr[j][e] + gi] * ql[j][e] : nullptr;
             }
 #pragma unroll
           for (int j = 0; j < FN; ++j)
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
             for (int e = 0; e < 2; ++e) {
               int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
               if (ii < t.mt && jj < t.nt && gi >= gj)
-                atomicAdd(arena + qb[j][e] + (i64)rp1[i] * ql[j][e], -acc[i][j][e]);
+                atomicAdd(reinterpret_cast<double*>(qb[j][e]) + (i64)rp1[i] * ql[j][e], -acc[i][j][e]);
             }
         }
       } else {
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
           for (int j = 0; j < FN; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              if (rp[j][e] >= 0) atomicAdd(arena + qb[j][e] + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+              if (rp[j][e] >= 0) atomicAdd(reinterpret_cast<double*>(qb[j][e]) + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
         }
       }
     }
@@ -1140,24 +1140,127 @@ __global__ void __launch_bounds__(DIAG_THREADS) k_bwd_diag(const SolveBcol* __re
   }
 }
 
-// ------------------------------------------------------------------------------ block-column pack / unpack
-// Multi-GPU exchange of one finished block column (rows x cols sub-matrix of a node, leading
-// dimension ld) through a contiguous staging buffer.
-__global__ void k_pack(const double* __restrict__ src, int ld, int rows, int cols, double* __restrict__ dst) {
-  i64 n = (i64)rows * cols;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-    i64 r = i / cols;
-    int c = (int)(i - r * cols);
-    dst[i] = src[r * ld + c];
+// ------------------------------------------------------------------------------ multi-GPU: peer memory
+// One rank per GPU; every rank maps every other rank's arena and flag block (CUDA IPC), so a
+// finished upper-tree block column is COPIED INTO THE PEERS' ARENAS by the owner's SMs over
+// NVLink (st.global on mapped peer pointers) and announced by a flag -- no staging buffer, no
+// pack / unpack, no library collective.  Flags carry the factorization's epoch (monotone), so
+// nothing is ever reset and captured graphs replay unchanged.
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long PEER_TIMEOUT_NS = 120ull * 1000000000ull;   // a peer that never shows up: trap, do not hang
+
+__global__ void k_epoch_inc(int* flags) { flags[F_EPOCH] += 1; }
+
+// rows x cols sub-matrix at `off` (leading dimension ld) of this rank's arena -> the same place in
+// every peer's arena, then flag `bc` := epoch on every peer (by the CTA that finishes last).
+__global__ void __launch_bounds__(256) k_push_bcol(PeerSet ps, i64 off, int ld, int rows, int cols, int bc,
+                                                   int* __restrict__ done) {
+  const double* src = ps.arena[ps.rank] + off;
+  const bool vec = ((cols | ld) & 1) == 0 && ((off & 1) == 0);
+  if (vec) {
+    const int c2 = cols >> 1;
+    const i64 n2 = (i64)rows * c2;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (i64)gridDim.x * blockDim.x) {
+      const i64 r = i / c2;
+      const int c = (int)(i - r * c2) * 2;
+      const double2 v = *reinterpret_cast<const double2*>(src + r * ld + c);
+      for (int p = 0; p < ps.world; ++p)
+        if (p != ps.rank) *reinterpret_cast<double2*>(ps.arena[p] + off + r * ld + c) = v;
+    }
+  } else {
+    const i64 n = (i64)rows * cols;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+      const i64 r = i / cols;
+      const int c = (int)(i - r * cols);
+      const double v = src[r * ld + c];
+      for (int p = 0; p < ps.world; ++p)
+        if (p != ps.rank) ps.arena[p][off + r * ld + c] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(done + bc, 1);
+    if (prev == (int)gridDim.x - 1) {
+      __threadfence_system();
+      const int epoch = ps.flags[ps.rank][F_EPOCH];
+      for (int p = 0; p < ps.world; ++p)
+        if (p != ps.rank) st_release_sys(ps.flags[p] + F_BCOL + bc, epoch);
+    }
   }
 }
-__global__ void k_unpack(double* __restrict__ dst, int ld, int rows, int cols, const double* __restrict__ src) {
-  i64 n = (i64)rows * cols;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-    i64 r = i / cols;
-    int c = (int)(i - r * cols);
-    dst[r * ld + c] = src[i];
+
+// the owner of block column `bc` has delivered it for the current factorization
+__global__ void k_wait_bcol(const int* flags, int bc) {
+  const int epoch = flags[F_EPOCH];
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flags + F_BCOL + bc) < epoch) {
+    __nanosleep(200);
+    if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+      printf("spllt_b200: timed out waiting for block column %d from its owner\n", bc);
+      __trap();
+    }
   }
+}
+
+// Barrier over the ranks (id = 1, 2, ... within a factorization).  what: 0 = arrive + wait,
+// 1 = arrive only, 2 = wait only (the single-GPU emulation of several ranks splits it, since kernels
+// of one GPU must never wait for kernels that are queued behind them).
+__global__ void k_rank_barrier(PeerSet ps, int id, int what) {
+  const int p = threadIdx.x;
+  if (p >= ps.world) return;
+  const int target = ps.flags[ps.rank][F_EPOCH] * 8 + id;
+  if (what != 2) {
+    __threadfence_system();
+    st_release_sys(ps.flags[p] + F_BAR + ps.rank, target);
+  }
+  if (what != 1) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(ps.flags[ps.rank] + F_BAR + p) < target) {
+      __nanosleep(200);
+      if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+        printf("spllt_b200: rank %d timed out in barrier %d waiting for rank %d\n", ps.rank, id, p);
+        __trap();
+      }
+    }
+  }
+}
+
+// max |a - b| and max |b| over the lower trapezoids of a list of nodes held in two arenas with
+// different layouts (multi-GPU factor against a single-GPU factor): out[0], out[1] as ordered bits
+struct CmpNode {
+  i64 off_a, off_b;
+  int m, n, ld;
+  int pad;
+};
+__global__ void k_compare_nodes(const CmpNode* __restrict__ nodes, const double* __restrict__ a,
+                                const double* __restrict__ b, unsigned long long* out) {
+  const CmpNode nd = nodes[blockIdx.x];
+  double dmax = 0.0, bmax = 0.0;
+  const i64 tot = (i64)nd.m * nd.n;
+  for (i64 i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int r = (int)(i / nd.n), c = (int)(i - (i64)r * nd.n);
+    if (c > r) continue;
+    const double x = a[nd.off_a + (i64)r * nd.ld + c], y = b[nd.off_b + (i64)r * nd.ld + c];
+    const double d = fabs(x - y);
+    dmax = (d > dmax || d != d) ? d : dmax;
+    bmax = fmax(bmax, fabs(y));
+  }
+  if (dmax != dmax) dmax = __longlong_as_double(0x7ff0000000000000LL);   // NaN -> +inf
+  atomicMax(out, (unsigned long long)__double_as_longlong(dmax));
+  atomicMax(out + 1, (unsigned long long)__double_as_longlong(bmax));
 }
 
 // ------------------------------------------------------------------------------ launchers
@@ -1225,13 +1328,19 @@ void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, D
     k_tile<64, 64, 32, 32, 2><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
 }
 
-void launch_pack(const double* src, int ld, int rows, int cols, double* dst, cudaStream_t st) {
-  i64 n = (i64)rows * cols;
-  if (n > 0) k_pack<<<(unsigned)std::min<i64>((n + 255) / 256, 148 * 8), 256, 0, st>>>(src, ld, rows, cols, dst);
+void launch_epoch_inc(int* flags, cudaStream_t st) { k_epoch_inc<<<1, 1, 0, st>>>(flags); }
+void launch_push_bcol(const PeerSet& ps, i64 off, int ld, int rows, int cols, int bc, int* done, cudaStream_t st) {
+  const i64 n = (i64)rows * cols / 2;
+  const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((n + 255) / 256, 148 * 4));
+  k_push_bcol<<<grid, 256, 0, st>>>(ps, off, ld, rows, cols, bc, done);
 }
-void launch_unpack(double* dst, int ld, int rows, int cols, const double* src, cudaStream_t st) {
-  i64 n = (i64)rows * cols;
-  if (n > 0) k_unpack<<<(unsigned)std::min<i64>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dst, ld, rows, cols, src);
+void launch_wait_bcol(const int* flags, int bc, cudaStream_t st) { k_wait_bcol<<<1, 1, 0, st>>>(flags, bc); }
+void launch_rank_barrier(const PeerSet& ps, int id, int what, cudaStream_t st) {
+  k_rank_barrier<<<1, 32, 0, st>>>(ps, id, what);
+}
+void launch_compare_nodes(const void* nodes, int count, const double* a, const double* b, unsigned long long* out,
+                          cudaStream_t st) {
+  if (count > 0) k_compare_nodes<<<count, 256, 0, st>>>((const CmpNode*)nodes, a, b, out);
 }
 
 void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st) {

@@ -7,7 +7,7 @@
 namespace spllt {
 
 struct DevMaps {          // inter-node update maps (device copies of Analysis::q_*)
-  const i64* q_base;
+  const i64* q_base;      // ABSOLUTE device address of the destination column (own or peer-mapped arena)
   const int* q_ld;
   const i64* q_rp;
   const int* rowpos;
@@ -29,8 +29,23 @@ void launch_tiles_tma_bg(const TileTask* tasks, i64 count, double* arena, DevMap
 void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
                       const void* tmaps, const void* tmaps_b, int bn, cudaStream_t st);
 
-void launch_pack(const double* src, int ld, int rows, int cols, double* dst, cudaStream_t st);
-void launch_unpack(double* dst, int ld, int rows, int cols, const double* src, cudaStream_t st);
+// ---- multi-GPU over peer-mapped memory (one rank per GPU)
+constexpr int MAX_RANKS = 8;
+// flag block of a rank (ints): [F_EPOCH] factorization counter (local), [F_BAR + r] barrier slot
+// written by rank r, [F_BCOL + g] epoch of the last delivery of global block column g
+constexpr int F_EPOCH = 0, F_BAR = 16, F_BCOL = 64;
+struct PeerSet {
+  int rank, world;
+  double* arena[MAX_RANKS];   // arena[rank] = own arena, the others are IPC mappings of the peers'
+  int* flags[MAX_RANKS];
+};
+void launch_epoch_inc(int* flags, cudaStream_t st);
+void launch_push_bcol(const PeerSet& ps, i64 off, int ld, int rows, int cols, int bc, int* done, cudaStream_t st);
+void launch_wait_bcol(const int* flags, int bc, cudaStream_t st);
+void launch_rank_barrier(const PeerSet& ps, int id, int what, cudaStream_t st);
+// nodes: device array of {i64 off_a, off_b; int m, n, ld, pad}; out[0] = max |a - b|, out[1] = max |b| (bits)
+void launch_compare_nodes(const void* nodes, int count, const double* a, const double* b, unsigned long long* out,
+                          cudaStream_t st);
 
 // solve
 void launch_permute_in(const double* x, int ldx, const int* porder, double* xw, int n, int nrhs, cudaStream_t st);

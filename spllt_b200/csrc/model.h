@@ -80,18 +80,27 @@ struct TileTask {
   int node, pad;     // source node (selects its TMA tensor map)
 };
 
-// L_EXCHANGE is not a kernel: it marks where the owner of a finished upper-tree block column
-// broadcasts it to the other ranks (begin = node, count = local block column, tag = owner rank)
-enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_EXCHANGE = 3, L_NKIND = 4 };
+// Multi-GPU (one rank per GPU, peer-mapped arenas, see Engine): the upper tree is walked in STEPS,
+// one per upper-tree block column, in the same global order on every rank.
+//   L_PUSH : this rank owns the block column of the step and has just factorized it: copy it into
+//            every peer's arena over NVLink and raise its flag there (begin = global block column)
+//   L_WAIT : another rank owns it: wait for the flag (begin = global block column)
+enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_PUSH = 3, L_WAIT = 4, L_NKIND = 5 };
 struct Launch {
   int kind;
-  int depth;
+  int depth;         // phase 0: panel slot; phase 1 (multi-GPU upper tree): step index
   i64 begin;         // first task in the list of this kind
   i64 count;         // tasks (= CTAs)
-  int phase;         // multi-GPU: 0 = subtrees owned by this rank, 1 = shared top of the tree
-  int tag;           // diagnostics: 0 panel, 4 updates on the critical path, 5 deferred inter-node updates
+  int phase;         // multi-GPU: 0 = subtrees owned by this rank, 1 = upper tree
+  int tag;           // 0 panel, 4 updates on the critical path, 5 deferred updates (previous step),
+                     // 7 urgent updates of a step (destinations whose turn comes next), 8 push, 9 wait
   int stream;        // 0 = main; 1 = background stream (deferred inter-node updates)
   int deadline;      // background launches: the slot whose panel launch must wait for them
+};
+struct TopStep {     // one upper-tree block column in the global step order
+  int node, c;       // node (0-based), local block column
+  int owner;         // rank that factorizes it and accumulates the updates into it
+  int slot;          // as-soon-as-possible panel slot of its first panel (sort key)
 };
 
 // ------------------------------------------------------------------ solve work lists
@@ -165,6 +174,9 @@ struct Analysis {
   int tile_n = 128;          // N extent of the large tiles: 128 (one CTA/SM) or 64 (two CTAs/SM)
   int dist_top = 0;          // multi-GPU: upper tree distributed block-column-cyclically (owner computes)
   std::vector<int> bcol_owner;  // [nbcol] rank that factorizes / receives the updates of a block column
+  std::vector<TopStep> top_steps;   // multi-GPU: upper-tree block columns in step order (same on every rank)
+  std::vector<int> bcol_step;       // [nbcol] step index of an upper-tree block column, -1 otherwise
+  i64 own_begin = 0, own_end = 0;   // arena slice holding the subtrees this rank owns
   i64 nnz = 0;               // entries of the user's lower triangle
   Symbolic sym;
   std::vector<int> porder;   // porder[p] = variable at pivot position p (0-based both)

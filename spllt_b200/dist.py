@@ -1,24 +1,34 @@
-"""One-process-per-GPU driver of the factorization (torch.distributed / NCCL is the plumbing).
+"""One-process-per-GPU driver of the distributed factorization / solve.
 
 world == 1: a thin pass-through to the C ABI.
 
-world > 1: subtrees of the assembly tree are dealt to ranks by proportional
-mapping; each rank factorizes its subtrees in its own HBM and accumulates their inter-node
-updates into its private copy of the upper tree; a sum all-reduce of the contiguous upper-tree
-slice of the arena over NVLink hands every rank the assembled upper tree.  The upper tree is then
-factorized block-column-cyclically, owner computes: a rank factorizes the block columns it owns
-and computes every update whose DESTINATION block column it owns; each finished block column is
-broadcast once by its owner (NCCL) before anybody uses it as a source.  No reductions in the
-upper tree.  (SPLLT_B200_REPLICATED_TOP=1: every rank factorizes the whole upper tree instead.)
+world > 1: everything numerical happens inside libspllt_b200.so -- this module only
+bootstraps the ranks (torch.distributed is the plumbing: it all-gathers the 128-byte CUDA IPC
+records of spllt_b200_comm_export so that every rank can map every peer's factor arena) and then
+calls the same entry points as on one GPU.
 
-Solve: see DistSpLLT.solve_dev -- subtree sweeps on their owners, the upper tree redundantly, two
-all-reduces of the work vector.
+Factorization (spllt_b200/csrc/analyse.cpp partition_tree / build_factor_schedule, engine.cu):
+  * subtrees of the assembly tree are dealt to the ranks by proportional mapping; each rank
+    factorizes its subtrees in its own HBM; their contributions into the upper tree are scattered
+    straight into the OWNING rank's arena by the update kernel's epilogue (RED.ADD.F64 on
+    peer-mapped addresses over NVLink) -- the reference's generated element
+    (src/spllt_factorization_mod.F90:224-237) never exists as a buffer, nothing is all-reduced;
+  * the upper tree is distributed by block column and walked in the same step order on every rank:
+    the owner of a step factorizes the block column (panel chain), copies it into every peer's
+    arena and raises its flag there; every rank applies it to the destination block columns it owns,
+    the ones whose own step comes next first (static look-ahead), so the next owner's panel chain
+    overlaps the other ranks' updates.  One in-order stream per rank, captured as one CUDA graph.
+
+Solve: see DistSpLLT.solve_dev -- subtree sweeps on their owners, the upper tree (whose factor every
+rank holds) redundantly, two all-reduces of the work vector.
 """
 import ctypes as C
 
 import numpy as np
 
 from .api import SpLLT, lib
+
+HANDLE_BYTES = 128
 
 
 class _DevArray:
@@ -33,9 +43,7 @@ class DistSpLLT:
         self.rank, self.world = rank, world
         self.local = SpLLT(nb=nb, ncpu=max(world, 1), **options)
         self.stream = stream
-        self.top = None
-        self.dist_top = False
-        self.program = []
+        self._single = None
 
     # -------------------------------------------------------------- phases
     def analyse(self, n, ptr, row):
@@ -44,88 +52,43 @@ class DistSpLLT:
         L = s.L
         if self.world > 1:
             L.spllt_b200_partition(s.akeep, s.fkeep, self.rank, self.world)
+            if self.stream is None:
+                # the collectives of the solve are ordered against torch's current stream only
+                import torch
+                self.stream = torch.cuda.current_stream()
         if self.stream is not None:
             s.set_stream(self.stream.cuda_stream)
         if self.world > 1:
-            import torch
-            b, e = C.c_longlong(0), C.c_longlong(0)
-            L.spllt_b200_shared_region(s.akeep, C.byref(b), C.byref(e))
-            self.top_range = (b.value, e.value)
-            base = L.spllt_b200_arena_ptr(s.fkeep)
-            if e.value > b.value:
-                self.top = torch.as_tensor(_DevArray(base + 8 * b.value, e.value - b.value), device="cuda")
-            self.dist_top = bool(L.spllt_b200_dist_top(s.akeep))
-            if self.dist_top:
-                self._build_program(base)
+            self._attach()
+        self._mat = (n, ptr, row)
         return flag
 
-    def _build_program(self, arena_base):
-        """Phase-1 program: runs of kernel launches separated by block-column broadcasts."""
+    def _attach(self):
+        """all-gather of the IPC records, then every rank maps every peer's arena and flag block"""
         import torch
+        import torch.distributed as dist
         s, L = self.local, self.local.L
-        nrec = L.spllt_b200_num_launch_records(s.akeep)
-        rec = np.zeros((max(nrec, 1), 8), dtype=np.int64)
-        L.spllt_b200_get_launch_records(s.akeep, rec.ctypes.data_as(C.POINTER(C.c_longlong)))
-        rec = rec[:nrec]
-        self.program = []
-        run_start = None
-        maxbuf = 0
-        off, ld, rows, cols = C.c_longlong(0), C.c_int(0), C.c_int(0), C.c_int(0)
-        for i in range(nrec):
-            kind, phase = int(rec[i, 0]), int(rec[i, 4])
-            if phase != 1:
-                continue
-            if kind == 3:
-                if run_start is not None:
-                    self.program.append(("run", run_start, i))
-                    run_start = None
-                node, c, owner = int(rec[i, 2]), int(rec[i, 3]), int(rec[i, 5])
-                L.spllt_b200_bcol_region(s.akeep, node + 1, c, C.byref(off), C.byref(ld), C.byref(rows), C.byref(cols))
-                self.program.append(("bcast", node + 1, c, owner, rows.value * cols.value))
-                maxbuf = max(maxbuf, rows.value * cols.value)
-            elif run_start is None:
-                run_start = i
-        if run_start is not None:
-            self.program.append(("run", run_start, nrec))
-        self.staging = torch.empty(max(maxbuf, 1), dtype=torch.float64, device="cuda")
+        mine = np.zeros(HANDLE_BYTES, dtype=np.uint8)
+        rc = L.spllt_b200_comm_export(s.fkeep, mine.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("spllt_b200_comm_export failed (%d)" % rc)
+        t = torch.from_numpy(mine).cuda()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t)
+        table = np.ascontiguousarray(torch.stack(out).cpu().numpy())
+        rc = L.spllt_b200_comm_attach(s.fkeep, self.rank, self.world, table.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("spllt_b200_comm_attach failed (%d)" % rc)
+        dist.barrier()    # nobody starts pushing before everybody has mapped everybody
 
     def factor_dev(self, d_val):
-        """d_val: torch CUDA tensor holding the user's val.  Asynchronous on the stream."""
-        s = self.local
-        if self.world == 1:
-            s.factor_dev(d_val.data_ptr())
-            return
-        import torch.distributed as dist
-        L = s.L
-        L.spllt_b200_factor_phase(s.akeep, s.fkeep, C.c_void_p(d_val.data_ptr()), 0)
-        if self.top is not None:
-            dist.all_reduce(self.top, op=dist.ReduceOp.SUM)     # the exchange step (NCCL over NVLink)
-        if not self.dist_top:
-            L.spllt_b200_factor_phase(s.akeep, s.fkeep, C.c_void_p(d_val.data_ptr()), 1)
-            return
-        for op in self.program:
-            if op[0] == "run":
-                L.spllt_b200_run_launches(s.fkeep, op[1], op[2])
-            else:
-                _, node, c, owner, count = op
-                buf = self.staging[:count]
-                if owner == self.rank:
-                    L.spllt_b200_pack_bcol(s.akeep, s.fkeep, node, c, C.c_void_p(buf.data_ptr()))
-                dist.broadcast(buf, src=owner)
-                if owner != self.rank:
-                    L.spllt_b200_unpack_bcol(s.akeep, s.fkeep, node, c, C.c_void_p(buf.data_ptr()))
+        """d_val: torch CUDA tensor holding the user's val.  Asynchronous on the stream; with several
+        ranks every rank calls it (the ranks meet inside the captured graph, not here)."""
+        self.local.factor_dev(d_val.data_ptr())
 
     def factor_host(self, val):
-        """Reference-facing call with a HOST val array (spllt_factor)."""
-        s = self.local
-        if self.world == 1:
-            s.factor(val)
-            return
-        import torch
-        if getattr(self, "_dval", None) is None or self._dval.numel() != val.size:
-            self._dval = torch.empty(val.size, dtype=torch.float64, device="cuda")
-        self._dval.copy_(torch.from_numpy(val), non_blocking=True)
-        self.factor_dev(self._dval)
+        """Reference-facing call with a HOST val array (spllt_factor: H2D copy + factorization)."""
+        self.local.factor(val)
 
     def solve_dev(self, d_x, nrhs=1):
         """d_x: torch CUDA tensor, nrhs x n (row r = right-hand side r, i.e. column-major n x nrhs);
@@ -142,6 +105,8 @@ class DistSpLLT:
         import torch
         import torch.distributed as dist
         L = s.L
+        assert torch.cuda.current_stream().cuda_stream == self.stream.cuda_stream, \
+            "the NCCL all-reduces are ordered against torch's current stream: make the engine's stream current"
         xw = torch.as_tensor(_DevArray(L.spllt_b200_xw_ptr(s.fkeep, nrhs), s.n * nrhs), device="cuda")
         px = C.c_void_p(d_x.data_ptr())
         L.spllt_b200_solve_phase(s.fkeep, nrhs, px, s.n, 0)
@@ -160,22 +125,57 @@ class DistSpLLT:
             torch.cuda.current_stream().synchronize()
 
     def pivot_flag(self):
-        return self.local.pivot_flag()
+        """0 = ok, else the smallest 1-based pivot column that failed on ANY rank."""
+        f = self.local.pivot_flag()
+        if self.world == 1:
+            return f
+        import torch
+        import torch.distributed as dist
+        big = 2 ** 31 - 1
+        t = torch.tensor([f if f > 0 else big], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        v = int(t.item())
+        return 0 if v == big else v
 
     def profile_factor(self, d_val):
-        """per-kernel-kind milliseconds of one un-graphed factorization (this rank's launches)"""
+        """per-kernel-kind milliseconds of one un-graphed factorization (this rank's launches).
+        Collective: with several ranks every rank must call it."""
         return self.local.profile_factor(d_val.data_ptr())
+
+    def compare_with_single_gpu(self, d_val):
+        """max relative difference between this rank's part of the distributed factor (its subtrees +
+        the upper tree) and a plain single-GPU factorization of the same matrix run on this rank's GPU;
+        the maximum over the ranks is returned on every rank.  Collective."""
+        import torch
+        import torch.distributed as dist
+        s = self.local
+        if self._single is None:
+            ref = SpLLT(nb=s.options.nb, ncpu=max(self.world, 1))
+            ref.analyse(*self._mat)
+            self._single = ref
+        ref = self._single
+        ref.factor_dev(d_val.data_ptr())
+        ref.wait()
+        self.wait()
+        out = np.zeros(2)
+        rc = s.L.spllt_b200_compare_factor(s.akeep, s.fkeep, ref.akeep, ref.fkeep, out.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc != 0 or out[1] <= 0:
+            raise RuntimeError("spllt_b200_compare_factor failed")
+        rel = float(out[0] / out[1])
+        if self.world > 1:
+            t = torch.tensor([rel], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rel = float(t.item())
+        return {"max_rel_diff": rel, "tol": 1e-12, "what": "every rank: entries of the nodes it holds (own subtrees + "
+                "upper tree) vs a single-GPU factorization on the same GPU; max over ranks"}
+
+    # -------------------------------------------------------------- reporting
+    def scaling(self):
+        return "strong"
 
     def solve_path(self):
         return ("multi-GPU: persistent pipelined kernels on the rank's subtrees, upper tree redundantly, "
                 "two NCCL all-reduces of the work vector")
-
-    # -------------------------------------------------------------- reporting
-    def work_multiplier(self):
-        return 1   # one factorization is shared by all ranks (strong scaling)
-
-    def scaling(self):
-        return "strong"
 
     def launches_per_factor(self):
         return int(self.local.L.spllt_b200_factor_launches(self.local.fkeep))
@@ -197,9 +197,9 @@ class DistSpLLT:
         top = float(per[own < 0].sum())
         mine = float(per[own == self.rank].sum())
         nsub = int(np.sum((own >= 0) & ((par >= s.nnodes) | (own[np.minimum(par, s.nnodes - 1)] < 0))))
-        how = ("distributed block-column-cyclically (owner computes, %d block-column broadcasts)"
-               % sum(1 for op in self.program if op[0] == "bcast")) if self.dist_top else "replicated"
-        return ("subtree->GPU proportional mapping (%d subtrees), sum all-reduce of the %.2f GB upper-tree "
-                "slice, upper tree (%.0f%% of flops) %s; rank %d subtree share %.1f%%"
-                % (nsub, (self.top_range[1] - self.top_range[0]) * 8 / 1e9, 100 * top / tot, how, self.rank,
-                   100 * mine / tot))
+        nsteps = int(s.L.spllt_b200_num_top_steps(s.akeep))
+        return ("subtree->GPU proportional mapping (%d subtrees; rank %d subtree share %.1f%% of flops); upper tree "
+                "(%.0f%% of flops) distributed by block column, owner computes, %d steps with static look-ahead; "
+                "subtree contributions scattered into the owner's HBM by peer RED.ADD.F64, finished block columns "
+                "pushed into the peers' arenas (CUDA IPC mappings over NVLink), no all-reduce"
+                % (nsub, self.rank, 100 * mine / tot, 100 * top / tot, nsteps))

@@ -110,6 +110,12 @@ module spllt_b200_iface
        integer(C_INT), intent(out) :: stat
      end subroutine c_spllt_deallocate_fkeep
 
+     function c_spllt_b200_num_factor(akeep) bind(C, name="spllt_b200_num_factor") result(f)
+       import
+       type(C_PTR), value :: akeep
+       integer(C_LONG_LONG) :: f
+     end function c_spllt_b200_num_factor
+
      !> 64-bit counters (include/spllt_b200.h): info%num_flops saturates at huge(0_C_INT)
      function c_spllt_b200_num_flops(akeep) bind(C, name="spllt_b200_num_flops") result(f)
        import

@@ -87,17 +87,15 @@ def main():
                             for c0 in range(0, int(nodes[k, 1] - nodes[k, 0] + 1), nb)) for k in range(nn)])
     assert np.array_equal(cnt[own == rank], npanels[own == rank]), "a block column of this rank is missing / duplicated"
     assert np.all(cnt[(own >= 0) & (own != rank)] == 0), "this rank schedules work on a foreign subtree"
-    # upper tree: replicated -> every rank holds every panel; distributed -> every panel exactly once overall
+    # upper tree: distributed by block column -> every panel exactly once over all ranks
     tsum = torch.from_numpy(cnt.copy())
     if not cpu:
         tsum = tsum.cuda()
     dist.all_reduce(tsum)
     tsum = tsum.cpu().numpy()
     top = own == -1
-    if s.L.spllt_b200_dist_top(s.akeep):
-        assert np.array_equal(tsum[top], npanels[top]), "an upper-tree panel is missing / duplicated across ranks"
-    else:
-        assert np.array_equal(cnt[top], npanels[top])
+    assert s.L.spllt_b200_dist_top(s.akeep) == 1
+    assert np.array_equal(tsum[top], npanels[top]), "an upper-tree panel is missing / duplicated across ranks"
     if cpu:
         dist.barrier()
         if rank == 0:
@@ -111,24 +109,39 @@ def main():
     d.wait()
     torch.cuda.synchronize()
     assert d.pivot_flag() == 0
+    for rep in range(2):          # graph replay: epochs / flags / counters carry over
+        d.factor_dev(d_val)
+        d.wait()
     ref = sp.SpLLT(nb=nb, ncpu=world)
     ref.analyse(n, ptr, row)
     ref.factor(val)
     ref.wait()
     worst = 0.0
+    blocks = s.blocks()
     for k in range(nn):
         if not mine[k]:
             continue
         ncol = int(nodes[k, 1] - nodes[k, 0] + 1)
-        bcol0 = int(s.blocks()[int(nodes[k, 6]) - 1, 7])
+        bcol0 = int(blocks[int(nodes[k, 6]) - 1, 7])
         for c in range(-(-ncol // nb)):
             a, b = s.lcol(bcol0 + c), ref.lcol(bcol0 + c)
             w = min(nb, ncol - c * nb)
             m = np.tril(np.ones((a.size // w, w), bool)).ravel()
             worst = max(worst, float(np.abs(a - b)[m].max() / max(np.abs(b).max(), 1e-300)))
     assert worst <= 1e-12, worst
+    cmpd = d.compare_with_single_gpu(d_val)      # the device-side comparison bench.py reports
+    assert cmpd["max_rel_diff"] <= 1e-12, cmpd
     t = torch.tensor([worst], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # a matrix that is not positive definite is reported on every rank, whoever owns the pivot
+    bad = val.copy()
+    bad[ptr[n // 2] - 1] = -1.0
+    d.factor_dev(torch.tensor(bad, device="cuda"))
+    d.wait()
+    assert d.pivot_flag() > 0
+    d.factor_dev(d_val)
+    d.wait()
+    assert d.pivot_flag() == 0
     # ---- distributed solve (subtree sweeps on their owners, upper tree redundantly, two all-reduces
     # of the work vector) vs the single-GPU solve and the reference's backward-error gate
     serr = 0.0
