@@ -649,7 +649,22 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
             flush_tiles(t, 4);
           }
         }
-        A.launches.push_back({L_PUSH, t, (i64)g, 1, 1, 8, 0, 0});
+        // delivery: first to the rank whose panel chain needs this block column next (the owner
+        // of the node's next block column, or of the ancestor block column its first row below
+        // maps to), then to everybody else -- the owner's NVLink egress is the bottleneck of a
+        // push (rows x w doubles to world - 1 peers), the next chain should not wait for all of it
+        int first = -1;
+        if (ts_.c + 1 < nd.nc) first = A.bcol_owner[g + 1];
+        else if (nd.m > nd.n) {
+          const int piv = A.index[nd.idx_off + nd.n];
+          const int a = A.col2node[piv];
+          first = A.bcol_owner[A.nodes[a].bcol0 + (piv - A.nodes[a].sa) / nb];
+        }
+        const int all = ((1 << A.world) - 1) & ~(1 << A.rank);
+        int m1 = (first >= 0 && first != A.rank) ? (1 << first) : 0;
+        if (getenv("SPLLT_B200_PUSH_ONESHOT")) m1 = 0;
+        if (m1) A.launches.push_back({L_PUSH, t, (i64)g, 0, 1, 8, 0, m1});
+        if (all & ~m1) A.launches.push_back({L_PUSH, t, (i64)g, 1, 1, 8, 0, all & ~m1});
       } else {
         flush_rest(t);
         A.launches.push_back({L_WAIT, t, (i64)g, 1, 1, 9, 0, 0});

@@ -66,7 +66,7 @@ void Engine::upload_tables() {
   CK(cudaMemset(arena, 0, std::max<i64>(S.arena, 1) * sizeof(double)));
   CK(cudaMalloc(&d_flags, (F_BCOL + std::max(S.nbcol, 1)) * sizeof(int)));
   CK(cudaMemset(d_flags, 0, (F_BCOL + std::max(S.nbcol, 1)) * sizeof(int)));
-  CK(cudaMalloc(&d_pushcnt, std::max(S.nbcol, 1) * sizeof(int)));
+  CK(cudaMalloc(&d_pushcnt, 2 * std::max(S.nbcol, 1) * sizeof(int)));
   if (S.world <= 1) {   // single GPU: the "peer set" is this arena
     peers = PeerSet{};
     peers.rank = 0;
@@ -280,14 +280,14 @@ void Engine::ensure_solve_buffers(int nrhs) {
 }
 
 void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
-  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos};
+  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos, A->world > 1 ? 1 : 0};
   switch (L.kind) {
     case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, d_counters + A->launches.size(), st); break;
     case L_PUSH: {
       const HNode& nd = A->nodes[A->bcol_node[L.begin]];
       const int r0 = A->bcol_c[L.begin] * A->nb;
-      launch_push_bcol(peers, nd.off + (i64)r0 * nd.ld + r0, nd.ld, nd.m - r0, std::min(A->nb, nd.n - r0), (int)L.begin,
-                       d_pushcnt, st);
+      launch_push_bcol(peers, (unsigned)L.deadline, nd.off + (i64)r0 * nd.ld + r0, nd.ld, nd.m - r0,
+                       std::min(A->nb, nd.n - r0), (int)L.begin, d_pushcnt + 2 * L.begin + L.count, st);
       break;
     }
     case L_WAIT: launch_wait_bcol(d_flags, (int)L.begin, st); break;
@@ -315,7 +315,7 @@ void Engine::factor_begin(const double* dval, cudaStream_t st) {
   if (S.world > 1) {
     if (S.own_end > S.own_begin) CK(cudaMemsetAsync(arena + S.own_begin, 0, (S.own_end - S.own_begin) * sizeof(double), st));
     if (S.arena > S.top_begin) CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
-    CK(cudaMemsetAsync(d_pushcnt, 0, std::max(S.nbcol, 1) * sizeof(int), st));
+    CK(cudaMemsetAsync(d_pushcnt, 0, 2 * std::max(S.nbcol, 1) * sizeof(int), st));
   } else {
     CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
   }

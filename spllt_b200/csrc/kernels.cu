@@ -48,6 +48,17 @@ __global__ void k_assemble(double* __restrict__ arena, const i64* __restrict__ d
   for (; i < cnt; i += stride) arena[dst[i]] = val[src[i]];
 }
 
+// Extend-add of one entry: fire-and-forget FP64 reduction at the destination's L2.  `addr` is an
+// absolute GLOBAL address (own arena or a peer's mapping); stating the state space keeps this one
+// REDG instruction (an atomicAdd on a generic pointer expands to a shared / global dispatch with a
+// returning ATOM).  sys: several GPUs may add into the same entry -> system scope.
+__device__ __forceinline__ void red_add_f64(i64 addr, double v, int sys) {
+  if (sys)
+    asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+  else
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -428,7 +439,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
       for (int j = 0; j < FN; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
-          if (rp[j][e] >= 0) atomicAdd(reinterpret_cast<double*>(qb[j][e]) + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+          if (rp[j][e] >= 0) red_add_f64(qb[j][e] + 8 * ((i64)rp[j][e] * ql[j][e]), -acc[i][j][e], mp.sys);
     }
   }
 }
@@ -732,7 +743,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
             for (int e = 0; e < 2; ++e) {
               int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
               if (ii < t.mt && jj < t.nt && gi >= gj)
-                atomicAdd(reinterpret_cast<double*>(qb[j][e]) + (i64)rp1[i] * ql[j][e], -acc[i][j][e]);
+                red_add_f64(qb[j][e] + 8 * ((i64)rp1[i] * ql[j][e]), -acc[i][j][e], mp.sys);
             }
         }
       } else {
@@ -752,7 +763,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
           for (int j = 0; j < FN; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              if (rp[j][e] >= 0) atomicAdd(reinterpret_cast<double*>(qb[j][e]) + (i64)rp[j][e] * ql[j][e], -acc[i][j][e]);
+              if (rp[j][e] >= 0) red_add_f64(qb[j][e] + 8 * ((i64)rp[j][e] * ql[j][e]), -acc[i][j][e], mp.sys);
         }
       }
     }
@@ -1165,7 +1176,7 @@ __global__ void k_epoch_inc(int* flags) { flags[F_EPOCH] += 1; }
 
 // rows x cols sub-matrix at `off` (leading dimension ld) of this rank's arena -> the same place in
 // every peer's arena, then flag `bc` := epoch on every peer (by the CTA that finishes last).
-__global__ void __launch_bounds__(256) k_push_bcol(PeerSet ps, i64 off, int ld, int rows, int cols, int bc,
+__global__ void __launch_bounds__(256) k_push_bcol(PeerSet ps, unsigned mask, i64 off, int ld, int rows, int cols, int bc,
                                                    int* __restrict__ done) {
   const double* src = ps.arena[ps.rank] + off;
   const bool vec = ((cols | ld) & 1) == 0 && ((off & 1) == 0);
@@ -1177,7 +1188,7 @@ __global__ void __launch_bounds__(256) k_push_bcol(PeerSet ps, i64 off, int ld, 
       const int c = (int)(i - r * c2) * 2;
       const double2 v = *reinterpret_cast<const double2*>(src + r * ld + c);
       for (int p = 0; p < ps.world; ++p)
-        if (p != ps.rank) *reinterpret_cast<double2*>(ps.arena[p] + off + r * ld + c) = v;
+        if (mask >> p & 1u) *reinterpret_cast<double2*>(ps.arena[p] + off + r * ld + c) = v;
     }
   } else {
     const i64 n = (i64)rows * cols;
@@ -1186,18 +1197,18 @@ __global__ void __launch_bounds__(256) k_push_bcol(PeerSet ps, i64 off, int ld, 
       const int c = (int)(i - r * cols);
       const double v = src[r * ld + c];
       for (int p = 0; p < ps.world; ++p)
-        if (p != ps.rank) ps.arena[p][off + r * ld + c] = v;
+        if (mask >> p & 1u) ps.arena[p][off + r * ld + c] = v;
     }
   }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int prev = atomicAdd(done + bc, 1);
+    const int prev = atomicAdd(done, 1);
     if (prev == (int)gridDim.x - 1) {
       __threadfence_system();
       const int epoch = ps.flags[ps.rank][F_EPOCH];
       for (int p = 0; p < ps.world; ++p)
-        if (p != ps.rank) st_release_sys(ps.flags[p] + F_BCOL + bc, epoch);
+        if (mask >> p & 1u) st_release_sys(ps.flags[p] + F_BCOL + bc, epoch);
     }
   }
 }
@@ -1329,10 +1340,11 @@ void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, D
 }
 
 void launch_epoch_inc(int* flags, cudaStream_t st) { k_epoch_inc<<<1, 1, 0, st>>>(flags); }
-void launch_push_bcol(const PeerSet& ps, i64 off, int ld, int rows, int cols, int bc, int* done, cudaStream_t st) {
+void launch_push_bcol(const PeerSet& ps, unsigned mask, i64 off, int ld, int rows, int cols, int bc, int* done,
+                      cudaStream_t st) {
   const i64 n = (i64)rows * cols / 2;
   const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((n + 255) / 256, 148 * 4));
-  k_push_bcol<<<grid, 256, 0, st>>>(ps, off, ld, rows, cols, bc, done);
+  k_push_bcol<<<grid, 256, 0, st>>>(ps, mask, off, ld, rows, cols, bc, done);
 }
 void launch_wait_bcol(const int* flags, int bc, cudaStream_t st) { k_wait_bcol<<<1, 1, 0, st>>>(flags, bc); }
 void launch_rank_barrier(const PeerSet& ps, int id, int what, cudaStream_t st) {

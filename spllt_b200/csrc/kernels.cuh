@@ -11,6 +11,7 @@ struct DevMaps {          // inter-node update maps (device copies of Analysis::
   const int* q_ld;
   const i64* q_rp;
   const int* rowpos;
+  int sys;                // 1: destinations may be written by several GPUs (system-scope reductions)
 };
 
 void kernels_init();      // opt-in shared memory sizes; call once per process
@@ -40,7 +41,9 @@ struct PeerSet {
   int* flags[MAX_RANKS];
 };
 void launch_epoch_inc(int* flags, cudaStream_t st);
-void launch_push_bcol(const PeerSet& ps, i64 off, int ld, int rows, int cols, int bc, int* done, cudaStream_t st);
+// mask: destination ranks; done: this push's own completion counter (zero at launch)
+void launch_push_bcol(const PeerSet& ps, unsigned mask, i64 off, int ld, int rows, int cols, int bc, int* done,
+                      cudaStream_t st);
 void launch_wait_bcol(const int* flags, int bc, cudaStream_t st);
 void launch_rank_barrier(const PeerSet& ps, int id, int what, cudaStream_t st);
 // nodes: device array of {i64 off_a, off_b; int m, n, ld, pad}; out[0] = max |a - b|, out[1] = max |b| (bits)

@@ -83,7 +83,8 @@ struct TileTask {
 // Multi-GPU (one rank per GPU, peer-mapped arenas, see Engine): the upper tree is walked in STEPS,
 // one per upper-tree block column, in the same global order on every rank.
 //   L_PUSH : this rank owns the block column of the step and has just factorized it: copy it into
-//            every peer's arena over NVLink and raise its flag there (begin = global block column)
+//            the arenas of the peers in the mask `deadline` over NVLink and raise its flag there
+//            (begin = global block column, count = 0 / 1: first / second push of the step)
 //   L_WAIT : another rank owns it: wait for the flag (begin = global block column)
 enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_PUSH = 3, L_WAIT = 4, L_NKIND = 5 };
 struct Launch {
