@@ -985,12 +985,13 @@ void build_solve_schedule(Analysis& A) {
   }
   A.sbcols.clear();
   A.supds.clear();
+  A.supds_t.clear();
   // two level-set schedules in the same lists: the nodes below the cut (companion of the
   // persistent kernels) and all nodes (many right-hand sides)
   for (int pass = 0; pass < 2; ++pass) {
     std::vector<SolveLaunch>& SL = pass == 0 ? A.slaunch : A.slaunch_full;
     const int cut = pass == 0 ? A.solve_cut : (1 << 30);
-    SL.assign(A.ndepth, SolveLaunch{0, 0, 0, 0});
+    SL.assign(A.ndepth, SolveLaunch{0, 0, 0, 0, 0, 0});
     std::vector<std::vector<int>> at(A.ndepth);
     for (int s = 0; s < nn; ++s)
       if (A.nodes[s].depth0 < cut)
@@ -999,6 +1000,7 @@ void build_solve_schedule(Analysis& A) {
       SolveLaunch& L = SL[d];
       L.diag_begin = A.sbcols.size();
       L.upd_begin = A.supds.size();
+      L.updt_begin = A.supds_t.size();
       for (int g : at[d]) {
         const HNode& nd = A.nodes[A.bcol_node[g]];
         SolveBcol b;
@@ -1014,9 +1016,12 @@ void build_solve_schedule(Analysis& A) {
         A.sbcols.push_back(b);
         for (int r = b.r0 + b.w; r < nd.m; r += SOLVE_ROWS)
           A.supds.push_back({id, r, std::min(SOLVE_ROWS, nd.m - r), 0});
+        for (int r = b.r0 + b.w; r < nd.m; r += SOLVE_ROWS_T)
+          for (int k0 = 0; k0 < b.w; k0 += 64) A.supds_t.push_back({id, r, std::min(SOLVE_ROWS_T, nd.m - r), k0});
       }
       L.diag_count = (i64)A.sbcols.size() - L.diag_begin;
       L.upd_count = (i64)A.supds.size() - L.upd_begin;
+      L.updt_count = (i64)A.supds_t.size() - L.updt_begin;
     }
   }
   build_pipe_schedule(A);

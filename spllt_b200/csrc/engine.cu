@@ -141,6 +141,7 @@ void Engine::upload_tables() {
   }
   d_sb = upload(S.sbcols);
   d_su = upload(S.supds);
+  d_sut = upload(S.supds_t);
   d_pnodes = upload(S.pnodes);
   {
     std::vector<PTaskD> td;
@@ -547,7 +548,10 @@ void Engine::enqueue_solve(int nrhs, int job, cudaStream_t st) {
                         S.nstrips, S.nnodes, S.n, d_psync + psync_ints, st);
     for (int d = S.ndepth - 1; d >= 0; --d) {
       const SolveLaunch& L = SL[d];
-      launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
+      if (solve_use_mma(nrhs, true))
+        launch_bwd_upd_mma(d_sut + L.updt_begin, L.updt_count, d_sb, arena, d_index, d_xw, nrhs, st);
+      else
+        launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
       launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
     }
   }
@@ -680,7 +684,10 @@ void Engine::profile_solve(double* dx, int ldx, int nrhs, double* ms6, const cha
   for (int d = S.ndepth - 1; d >= 0; --d) {
     const SolveLaunch& L = SL[d];
     if (L.diag_count == 0 && L.upd_count == 0) continue;
-    launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
+    if (solve_use_mma(nrhs, true))
+        launch_bwd_upd_mma(d_sut + L.updt_begin, L.updt_count, d_sb, arena, d_index, d_xw, nrhs, st);
+      else
+        launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, st);
     mark();
     recs.push_back({2, d, L.upd_count});
     launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, st);
@@ -728,7 +735,10 @@ void Engine::trace_solve(double* dx, int ldx, int nrhs, unsigned long long* out_
                     S.nstrips, S.nnodes, S.n, d_psync + psync_ints, stream, tb);
   for (int d = S.ndepth - 1; d >= 0; --d) {
     const SolveLaunch& L = S.slaunch[d];
-    launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
+    if (solve_use_mma(nrhs, true))
+      launch_bwd_upd_mma(d_sut + L.updt_begin, L.updt_count, d_sb, arena, d_index, d_xw, nrhs, stream);
+    else
+      launch_bwd_upd(d_su + L.upd_begin, L.upd_count, d_sb, arena, d_index, d_xw, nrhs, stream);
     launch_bwd_diag(d_sb + L.diag_begin, L.diag_count, arena, d_xw, nrhs, stream);
   }
   launch_permute_out(dx, ldx, d_porder, d_xw, S.n, nrhs, stream);
@@ -810,6 +820,7 @@ void Engine::release() {
   d_tmaps = d_tmaps_b = nullptr;
   cudaFree(d_sb);
   cudaFree(d_su);
+  cudaFree(d_sut);
   cudaFree(d_pnodes);
   cudaFree(d_ptask_f);
   cudaFree(d_ptask_b);

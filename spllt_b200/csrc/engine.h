@@ -55,6 +55,7 @@ struct Engine {
   void* d_tmaps_b = nullptr;  // same with tile_n-row boxes (B operand)
   SolveBcol* d_sb = nullptr;
   SolveUpd* d_su = nullptr;
+  SolveUpdT* d_sut = nullptr;     // backward update tasks of the DMMA path (many right-hand sides)
   PNode* d_pnodes = nullptr;      // pipelined solve tables (solve_pipe.cu)
   PTaskD* d_ptask_f = nullptr;    // task + node records, forward / backward order
   PTaskD* d_ptask_b = nullptr;

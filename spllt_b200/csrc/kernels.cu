@@ -52,8 +52,9 @@ __global__ void k_assemble(double* __restrict__ arena, const i64* __restrict__ d
 // absolute GLOBAL address (own arena or a peer's mapping); stating the state space keeps this one
 // REDG instruction (an atomicAdd on a generic pointer expands to a shared / global dispatch with a
 // returning ATOM).  sys: several GPUs may add into the same entry -> system scope.
-__device__ __forceinline__ void red_add_f64(i64 addr, double v, int sys) {
-  if (sys)
+template <bool SYS>
+__device__ __forceinline__ void red_add_f64(i64 addr, double v) {
+  if (SYS)
     asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
   else
     asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(PANEL_THREADS) k_panel(const PanelTask* __rest
 constexpr int KC = 32;          // K chunk per pipeline stage
 constexpr int SLD = KC + 4;     // padded shared row: (r*SLD + k) mod 16 distinct for r<4, k<4
 
-template <int BM, int BN, int WM, int WN, int NSTAGE>
+template <int BM, int BN, int WM, int WN, int NSTAGE, bool SYS>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
     k_tile(const TileTask* __restrict__ tasks, double* __restrict__ arena, DevMaps mp) {
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
       for (int j = 0; j < FN; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
-          if (rp[j][e] >= 0) red_add_f64(qb[j][e] + 8 * ((i64)rp[j][e] * ql[j][e]), -acc[i][j][e], mp.sys);
+          if (rp[j][e] >= 0) red_add_f64<SYS>(qb[j][e] + 8 * ((i64)rp[j][e] * ql[j][e]), -acc[i][j][e]);
     }
   }
 }
@@ -485,7 +486,7 @@ struct StageHdr {   // what a filled stage contains
 // BN = 128: 8 consumer warps + producer warpgroup = 384 threads, 3 stages, one CTA per SM.
 // BN = 64 : 4 consumer warps + producer warpgroup = 256 threads, 2 stages, TWO CTAs per SM: while
 //           one CTA runs the (DMMA-idle) scatter epilogue of a tile the other keeps the pipe busy.
-template <int BN, int TM_ST>
+template <int BN, int TM_ST, bool SYS>
 __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
     k_tile_tma(const TileTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, double* __restrict__ arena,
                DevMaps mp, const unsigned char* __restrict__ tmaps, const unsigned char* __restrict__ tmaps_b) {
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
             for (int e = 0; e < 2; ++e) {
               int jj = wn0 + j * 8 + (e ? cj1 : cj0), gj = t.j0 + jj;
               if (ii < t.mt && jj < t.nt && gi >= gj)
-                red_add_f64(qb[j][e] + 8 * ((i64)rp1[i] * ql[j][e]), -acc[i][j][e], mp.sys);
+                red_add_f64<SYS>(qb[j][e] + 8 * ((i64)rp1[i] * ql[j][e]), -acc[i][j][e]);
             }
         }
       } else {
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(BN == 128 ? 384 : 256, BN == 128 ? 1 : 2)
           for (int j = 0; j < FN; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              if (rp[j][e] >= 0) red_add_f64(qb[j][e] + 8 * ((i64)rp[j][e] * ql[j][e]), -acc[i][j][e], mp.sys);
+              if (rp[j][e] >= 0) red_add_f64<SYS>(qb[j][e] + 8 * ((i64)rp[j][e] * ql[j][e]), -acc[i][j][e]);
         }
       }
     }
@@ -1065,6 +1066,201 @@ __global__ void __launch_bounds__(256) k_bwd_upd(const SolveUpd* __restrict__ up
   }
 }
 
+// ------------------------------------------------------------------------------ many right-hand sides: DMMA tiles
+// With nrhs >= 16 the updates below a block column are GEMMs (the reference switches to dgemm there,
+// src/spllt_solve_kernels_mod.F90:108-130, :185-202): L tile x X block on the FP64 tensor pipe
+// (mma.sync.m8n8k4, SASS DMMA.8x8x4) instead of 8 right-hand sides per pass on scalar FMAs.
+// Work vector: row-major n x nrhs, so a row of X / Y is one contiguous run of nrhs doubles.
+constexpr int MQ = 64;          // right-hand sides per CTA pass
+constexpr int MKC = 32;         // contraction chunk per pipeline stage
+constexpr int MLD_A = MKC + 4;  // [64 rows][MKC]: (row * 36 + k) mod 16 distinct for a half-warp
+constexpr int MLD_B = MQ + 4;   // [MKC][MQ]:      (k * 68 + q)  mod 16 distinct for a half-warp
+constexpr int MST = 3;          // stages
+constexpr int SMEM_FWD_MMA = MST * (64 * MLD_A + MKC * MLD_B) * 8;
+constexpr int SMEM_BWD_MMA = MST * (2 * MKC * MLD_B) * 8;
+
+// Forward: xw[index[r], :] -= L[r, bcol] * X_bcol for one 64-row chunk, MQ right-hand sides.
+// 4 warps, warp tile 32 rows x 32 right-hand sides (16 DMMA per 8 fragment loads and 4-k step).
+__global__ void __launch_bounds__(128) k_fwd_upd_mma(const SolveUpd* __restrict__ ups, const SolveBcol* __restrict__ bcs,
+                                                     const double* __restrict__ arena, const int* __restrict__ index,
+                                                     double* __restrict__ xw, int nrhs) {
+  extern __shared__ __align__(16) double sm[];
+  double* As = sm;                          // [MST][64][MLD_A]   L rows, k contiguous
+  double* Bs = sm + MST * 64 * MLD_A;       // [MST][MKC][MLD_B]  X rows (k), right-hand sides contiguous
+  const SolveUpd u = ups[blockIdx.x];
+  const SolveBcol b = bcs[u.bc];
+  const int w = b.w, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rc0 = blockIdx.y * MQ, nr = min(MQ, nrhs - rc0);
+  const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;
+  const double* L = arena + b.off + (i64)u.r * b.ld + b.r0;
+  const double* X = xw + (i64)(b.sa + b.r0) * nrhs + rc0;
+  const bool al = (b.r0 & 1) == 0;
+  const int nch = (w + MKC - 1) / MKC;
+  auto load_stage = [&](int ch, int st) {
+    const int kb = ch * MKC;
+    // A: 64 rows x MKC, pairs of doubles
+    for (int c = tid; c < 64 * (MKC / 2); c += 128) {
+      const int r = c / (MKC / 2), q = (c % (MKC / 2)) * 2;
+      double* d = As + (st * 64 + r) * MLD_A + q;
+      const int k = kb + q;
+      const int valid = r < u.nrows ? min(max(w - k, 0), 2) : 0;
+      const double* g = L + (i64)min(r, u.nrows - 1) * b.ld + k;
+      if (al) {
+        cp_async16(d, valid ? g : L, valid * 8);
+      } else {
+        cp_async8(d, valid > 0 ? g : L, valid > 0 ? 8 : 0);
+        cp_async8(d + 1, valid > 1 ? g + 1 : L, valid > 1 ? 8 : 0);
+      }
+    }
+    // B: MKC rows of X x MQ right-hand sides (nrhs is even: 16-byte pieces)
+    for (int c = tid; c < MKC * (MQ / 2); c += 128) {
+      const int k = c / (MQ / 2), q = (c % (MQ / 2)) * 2;
+      double* d = Bs + (st * MKC + k) * MLD_B + q;
+      const int valid = (kb + k < w) ? min(max(nr - q, 0), 2) : 0;
+      cp_async16(d, valid ? X + (i64)(kb + k) * nrhs + q : X, valid * 8);
+    }
+  };
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < MST - 1; ++s) {
+    if (s < nch) load_stage(s, s);
+    cp_commit();
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    cp_wait<MST - 2>();
+    __syncthreads();
+    const int nx = ch + MST - 1;
+    if (nx < nch) load_stage(nx, nx % MST);
+    cp_commit();
+    const double* a = As + ((ch % MST) * 64 + wm0 + (lane >> 2)) * MLD_A + (lane & 3);
+    const double* bq = Bs + ((ch % MST) * MKC + (lane & 3)) * MLD_B + wn0 + (lane >> 2);
+#pragma unroll
+    for (int k4 = 0; k4 < MKC; k4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = a[i * 8 * MLD_A + k4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bq[k4 * MLD_B + j * 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_wait<0>();
+  // scatter: accumulator (row 8 i + lane / 4, right-hand sides 8 j + 2 (lane % 4) + {0, 1})
+  const int* idx = index + b.idx_off + u.r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = wm0 + i * 8 + (lane >> 2);
+    if (row >= u.nrows) continue;
+    double* dst = xw + (i64)idx[row] * nrhs + rc0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = wn0 + j * 8 + 2 * (lane & 3) + e;
+        if (q < nr) atomicAdd(dst + q, -acc[i][j][e]);
+      }
+  }
+}
+
+// Backward: X_bcol[k0 .. k0+64, :] -= L[rows, k0 .. k0+64]^T * xw[index[rows], :] for up to 512
+// rows of a block column (the sums stay in registers over all of them: one reduction per entry
+// and task).  The contraction runs over ROWS, so both operands are staged row by row.
+__global__ void __launch_bounds__(128) k_bwd_upd_mma(const SolveUpdT* __restrict__ ups, const SolveBcol* __restrict__ bcs,
+                                                     const double* __restrict__ arena, const int* __restrict__ index,
+                                                     double* __restrict__ xw, int nrhs) {
+  extern __shared__ __align__(16) double sm[];
+  double* Ls = sm;                          // [MST][MKC rows][MLD_B]  L rows, columns k0.. contiguous
+  double* Ys = sm + MST * MKC * MLD_B;      // [MST][MKC rows][MLD_B]  gathered rows of the work vector
+  const SolveUpdT u = ups[blockIdx.x];
+  const SolveBcol b = bcs[u.bc];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rc0 = blockIdx.y * MQ, nr = min(MQ, nrhs - rc0);
+  const int kw = min(64, b.w - u.k0);       // valid columns of this tile
+  const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;
+  const double* L = arena + b.off + (i64)u.r * b.ld + b.r0 + u.k0;
+  const int* idx = index + b.idx_off + u.r;
+  const bool al = ((b.r0 + u.k0) & 1) == 0;
+  const int nch = (u.nrows + MKC - 1) / MKC;
+  auto load_stage = [&](int ch, int st) {
+    const int rb = ch * MKC;
+    for (int c = tid; c < MKC * 32; c += 128) {
+      const int r = c >> 5, q = (c & 31) * 2;
+      const bool rok = rb + r < u.nrows;
+      const int row = min(rb + r, u.nrows - 1);
+      {
+        double* d = Ls + (st * MKC + r) * MLD_B + q;
+        const int valid = rok ? min(max(kw - q, 0), 2) : 0;
+        const double* g = L + (i64)row * b.ld + q;
+        if (al) {
+          cp_async16(d, valid ? g : L, valid * 8);
+        } else {
+          cp_async8(d, valid > 0 ? g : L, valid > 0 ? 8 : 0);
+          cp_async8(d + 1, valid > 1 ? g + 1 : L, valid > 1 ? 8 : 0);
+        }
+      }
+      {
+        double* d = Ys + (st * MKC + r) * MLD_B + q;
+        const int valid = rok ? min(max(nr - q, 0), 2) : 0;
+        const double* g = xw + (i64)idx[row] * nrhs + rc0 + q;
+        cp_async16(d, valid ? g : xw, valid * 8);
+      }
+    }
+  };
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < MST - 1; ++s) {
+    if (s < nch) load_stage(s, s);
+    cp_commit();
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    cp_wait<MST - 2>();
+    __syncthreads();
+    const int nx = ch + MST - 1;
+    if (nx < nch) load_stage(nx, nx % MST);
+    cp_commit();
+    // A fragment (m = column k, kk = row r) = L[r][k]; B fragment (kk = row r, n = q) = Y[r][q]
+    const double* a = Ls + ((ch % MST) * MKC + (lane & 3)) * MLD_B + wm0 + (lane >> 2);
+    const double* bq = Ys + ((ch % MST) * MKC + (lane & 3)) * MLD_B + wn0 + (lane >> 2);
+#pragma unroll
+    for (int r4 = 0; r4 < MKC; r4 += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = a[r4 * MLD_B + i * 8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = bq[r4 * MLD_B + j * 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_wait<0>();
+  double* xg = xw + (i64)(b.sa + b.r0 + u.k0) * nrhs + rc0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = wm0 + i * 8 + (lane >> 2);
+    if (k >= kw) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = wn0 + j * 8 + 2 * (lane & 3) + e;
+        if (q < nr) atomicAdd(xg + (i64)k * nrhs + q, -acc[i][j][e]);
+      }
+  }
+}
+
 // Backward: solve L_cc^T x = b, panels from last to first, right-looking: (a) transposed
 // triangular solve of the 64 x 64 diagonal block (fetched with cp.async during the previous
 // panel's update); (b) x[0..p0) -= L[p rows, 0..p0)^T x_p: thread per column, coalesced across
@@ -1283,16 +1479,22 @@ constexpr int SMEM_SOLVE_MAX = 200 * 1024;
 void kernels_init() {
   CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
   CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_PANEL));
-  CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
-  CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
-  CK(cudaFuncSetAttribute(k_tile_tma<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(128, 3)));
-  CK(cudaFuncSetAttribute(k_tile_tma<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_BG));
+  CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
+  CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
+  CK(cudaFuncSetAttribute(k_tile_tma<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(128, 3)));
+  CK(cudaFuncSetAttribute(k_tile_tma<64, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_BG));
+  CK(cudaFuncSetAttribute(k_tile<64, 64, 32, 32, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_S));
+  CK(cudaFuncSetAttribute(k_tile<128, 128, 64, 32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_L));
+  CK(cudaFuncSetAttribute(k_tile_tma<128, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tm_smem(128, 3)));
+  CK(cudaFuncSetAttribute(k_tile_tma<64, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TILE_BG));
   CK(cudaFuncSetAttribute(k_fwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_bwd_diag<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_bwd_diag<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_upd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
   CK(cudaFuncSetAttribute(k_fwd_upd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SOLVE_MAX));
+  CK(cudaFuncSetAttribute(k_fwd_upd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD_MMA));
+  CK(cudaFuncSetAttribute(k_bwd_upd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_MMA));
 }
 
 void launch_assemble(double* arena, const i64* dst, const i64* src, const double* val, i64 cnt, cudaStream_t st) {
@@ -1311,14 +1513,19 @@ void launch_panel_dbg(const PanelTask* tasks, i64 count, double* arena, int* inf
 void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* arena, DevMaps maps,
                       const void* tmaps, const void* tmaps_b, int bn, cudaStream_t st) {
   if (count <= 0) return;
+  const unsigned char *tm = (const unsigned char*)tmaps, *tb = (const unsigned char*)tmaps_b;
   if (bn == 128) {
     unsigned grid = (unsigned)std::min<i64>(count, 148);
-    k_tile_tma<128, 3><<<grid, 384, tm_smem(128, 3), st>>>(tasks, (int)count, counter, arena, maps,
-                                                          (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
+    if (maps.sys)
+      k_tile_tma<128, 3, true><<<grid, 384, tm_smem(128, 3), st>>>(tasks, (int)count, counter, arena, maps, tm, tb);
+    else
+      k_tile_tma<128, 3, false><<<grid, 384, tm_smem(128, 3), st>>>(tasks, (int)count, counter, arena, maps, tm, tb);
   } else {
     unsigned grid = (unsigned)std::min<i64>(count, 296);
-    k_tile_tma<64, 2><<<grid, 256, tm_smem(64, 2), st>>>(tasks, (int)count, counter, arena, maps,
-                                                        (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
+    if (maps.sys)
+      k_tile_tma<64, 2, true><<<grid, 256, tm_smem(64, 2), st>>>(tasks, (int)count, counter, arena, maps, tm, tb);
+    else
+      k_tile_tma<64, 2, false><<<grid, 256, tm_smem(64, 2), st>>>(tasks, (int)count, counter, arena, maps, tm, tb);
   }
 }
 // Background variant (deferred inter-node updates on the low-priority stream): one tile per
@@ -1328,15 +1535,25 @@ void launch_tiles_tma(const TileTask* tasks, i64 count, int* counter, double* ar
 void launch_tiles_tma_bg(const TileTask* tasks, i64 count, double* arena, DevMaps maps, const void* tmaps,
                          const void* tmaps_b, cudaStream_t st) {
   if (count <= 0) return;
-  k_tile_tma<64, 2><<<(unsigned)count, 256, tm_smem(64, 2), st>>>(tasks, (int)count, nullptr, arena, maps,
-                                                               (const unsigned char*)tmaps, (const unsigned char*)tmaps_b);
+  const unsigned char *tm = (const unsigned char*)tmaps, *tb = (const unsigned char*)tmaps_b;
+  if (maps.sys)
+    k_tile_tma<64, 2, true><<<(unsigned)count, 256, tm_smem(64, 2), st>>>(tasks, (int)count, nullptr, arena, maps, tm, tb);
+  else
+    k_tile_tma<64, 2, false><<<(unsigned)count, 256, tm_smem(64, 2), st>>>(tasks, (int)count, nullptr, arena, maps, tm, tb);
 }
 void launch_tiles(const TileTask* tasks, i64 count, bool large, double* arena, DevMaps maps, cudaStream_t st) {
   if (count <= 0) return;
-  if (large)
-    k_tile<128, 128, 64, 32, 3><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
-  else
-    k_tile<64, 64, 32, 32, 2><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
+  if (large) {
+    if (maps.sys)
+      k_tile<128, 128, 64, 32, 3, true><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
+    else
+      k_tile<128, 128, 64, 32, 3, false><<<(unsigned)count, 256, SMEM_TILE_L, st>>>(tasks, arena, maps);
+  } else {
+    if (maps.sys)
+      k_tile<64, 64, 32, 32, 2, true><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
+    else
+      k_tile<64, 64, 32, 32, 2, false><<<(unsigned)count, 128, SMEM_TILE_S, st>>>(tasks, arena, maps);
+  }
 }
 
 void launch_epoch_inc(int* flags, cudaStream_t st) { k_epoch_inc<<<1, 1, 0, st>>>(flags); }
@@ -1387,11 +1604,27 @@ void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double
 void launch_fwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
                     double* xw, int nrhs, cudaStream_t st) {
   if (count <= 0) return;
+  if (solve_use_mma(nrhs, false)) {
+    k_fwd_upd_mma<<<dim3((unsigned)count, (nrhs + MQ - 1) / MQ), 128, SMEM_FWD_MMA, st>>>(up, bc, arena, index, xw, nrhs);
+    return;
+  }
   if (nrhs == 1)
     k_fwd_upd<1><<<dim3((unsigned)count, 1), 256, solve_smem(g_maxw, 1, false), st>>>(up, bc, arena, index, xw, nrhs);
   else
     k_fwd_upd<8><<<dim3((unsigned)count, (nrhs + 7) / 8), 256, solve_smem(g_maxw, 8, false), st>>>(up, bc, arena, index,
                                                                                                  xw, nrhs);
+}
+// Forward updates pay off from 16 right-hand sides; the backward tiles are 64 right-hand sides wide
+// and only pay off when at least half of a tile is used (measured on Poisson 80^3: nrhs = 16:
+// forward 6.0 -> 3.3 ms, backward 4.5 -> 5.2 ms; nrhs = 64: 20.4 -> 3.5 ms and 11.8 -> 5.2 ms).
+bool solve_use_mma(int nrhs, bool backward) {
+  static const bool off = getenv("SPLLT_B200_SOLVE_NO_MMA") != nullptr;
+  return !off && nrhs >= (backward ? 32 : 16) && (nrhs & 1) == 0;
+}
+void launch_bwd_upd_mma(const SolveUpdT* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
+                        double* xw, int nrhs, cudaStream_t st) {
+  if (count <= 0) return;
+  k_bwd_upd_mma<<<dim3((unsigned)count, (nrhs + MQ - 1) / MQ), 128, SMEM_BWD_MMA, st>>>(up, bc, arena, index, xw, nrhs);
 }
 void launch_bwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
                     double* xw, int nrhs, cudaStream_t st) {

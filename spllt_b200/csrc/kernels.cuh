@@ -59,6 +59,11 @@ void launch_fwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const do
 void launch_bwd_upd(const SolveUpd* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
                     double* xw, int nrhs, cudaStream_t st);
 void launch_bwd_diag(const SolveBcol* bc, i64 count, const double* arena, double* xw, int nrhs, cudaStream_t st);
+// many right-hand sides (nrhs >= 16, even): the updates run on DMMA tiles.  launch_fwd_upd switches by
+// itself (same 64-row chunks); the backward update has its own task list (up to 512 rows x 64 columns)
+bool solve_use_mma(int nrhs, bool backward);
+void launch_bwd_upd_mma(const SolveUpdT* up, i64 count, const SolveBcol* bc, const double* arena, const int* index,
+                        double* xw, int nrhs, cudaStream_t st);
 
 // pipelined solve (solve_pipe.cu): one persistent kernel per sweep
 constexpr int PIPE_RC = 4;   // right-hand sides per pass when nrhs > 1

@@ -117,9 +117,14 @@ struct SolveBcol {
 struct SolveUpd {    // rows [r, r+nrows) of block column `bc` (index into the SolveBcol list)
   int bc, r, nrows, pad;
 };
+struct SolveUpdT {   // backward update on DMMA tiles: rows [r, r+nrows) x columns [k0, k0+64) of block column `bc`
+  int bc, r, nrows, k0;
+};
+constexpr int SOLVE_ROWS_T = 512;   // rows per SolveUpdT task
 struct SolveLaunch {
   i64 diag_begin, diag_count;   // SolveBcol range
   i64 upd_begin, upd_count;     // SolveUpd range
+  i64 updt_begin, updt_count;   // SolveUpdT range (many right-hand sides)
 };
 
 // ------------------------------------------------------------------ pipelined solve (solve_pipe.cu)
@@ -217,6 +222,7 @@ struct Analysis {
   // solve schedule (forward order; the backward sweep walks it in reverse)
   std::vector<SolveBcol> sbcols;
   std::vector<SolveUpd> supds;
+  std::vector<SolveUpdT> supds_t;
   std::vector<SolveLaunch> slaunch;   // one per depth: nodes below solve_cut (none by default)
   std::vector<SolveLaunch> slaunch_full;  // one per depth: ALL nodes (used when nrhs > pipe_max_nrhs)
   int pipe_max_nrhs = 8;              // more right-hand sides than this: level-set launches (RC = 8 kernels)

@@ -140,7 +140,9 @@ class DistSpLLT:
     def profile_factor(self, d_val):
         """per-kernel-kind milliseconds of one un-graphed factorization (this rank's launches).
         Collective: with several ranks every rank must call it."""
-        return self.local.profile_factor(d_val.data_ptr())
+        import os
+        csv = os.environ.get("SPLLT_BENCH_PROFILE_CSV")     # diagnostics: one line per launch, per rank
+        return self.local.profile_factor(d_val.data_ptr(), "%s.rank%d.csv" % (csv, self.rank) if csv else None)
 
     def compare_with_single_gpu(self, d_val):
         """max relative difference between this rank's part of the distributed factor (its subtrees +
