@@ -514,6 +514,22 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
     for (size_t q = g0; q < A.panel_tasks.size(); ++q) A.panel_tasks[q].ngroup = (int)(A.panel_tasks.size() - g0);
   };
 
+  // a3 inside a block column, TWO-LEVEL blocking.  Updating every remaining column of the block
+  // column after each 64-column panel (K = 64) makes the block column pass through HBM
+  // w / 128 times (11x read-modify-write amplification at w = 768) in tiles that do 1 MFLOP per
+  // 128 KB moved -- measured 8 TF/s, 30 % of a Poisson 100^3 factorization for 12 % of its flops.
+  // Instead the panel only updates the rest of its MID-BLOCK (mid_w = 256 columns); when a
+  // mid-block is complete, ONE K = mid_w update brings the block column's later columns up to
+  // date.  Same arithmetic on every entry (right-looking, every update applied before the
+  // entry's own panel), 2.2x less traffic, and most of those flops move to K = 256 tiles.
+  const int mid_w = std::max(IB, (getenv("SPLLT_B200_MID_BLOCK") ? atoi(getenv("SPLLT_B200_MID_BLOCK")) : 256) / IB * IB);
+  auto inner_updates = [&](const HNode& nd, int r0, int w, int k0, int pw) {
+    const int bend = r0 + w;
+    const int mb0 = r0 + (k0 - r0) / mid_w * mid_w, me = std::min(mb0 + mid_w, bend);
+    if (k0 + pw < me) add_tiles(A, ts, tl, nd, k0 + pw, me, 0, nd.m, k0, pw, -1, tile_l_min);
+    else if (me < bend) add_tiles(A, ts, tl, nd, me, bend, 0, nd.m, mb0, me - mb0, -1, tile_l_min);
+  };
+
   // ---- phase 0: every node on one GPU; the subtrees this rank owns on several
   {
     const int phase = 0;
@@ -556,8 +572,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         int k0 = r0 + st.p * IB;
         const bool last_in_bcol = k0 + pw >= r0 + w;
         emit_panel(nd, k0, pw);
-        // a3 inside the block column: the columns right of this panel (K = pw)
-        if (!last_in_bcol) add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+        inner_updates(nd, r0, w, k0, pw);   // a3 inside the block column (two-level blocking)
         if (last_in_bcol) {
           // a3: the finished block column updates the node's later block columns (K = w)
           if (st.c + 1 < nd.nc) add_tiles(A, ts, tl, nd, r0 + w, nd.n, 0, nd.m, r0, w, -1, tile_l_min);
@@ -645,7 +660,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
           emit_panel(nd, k0, pw);
           A.launches.push_back({L_PANEL, t, p0, (i64)A.panel_tasks.size() - p0, 1, 0, 0, 0});
           if (k0 + pw < r0 + w) {
-            add_tiles(A, ts, tl, nd, k0 + pw, r0 + w, 0, nd.m, k0, pw, -1, tile_l_min);
+            inner_updates(nd, r0, w, k0, pw);
             flush_tiles(t, 4);
           }
         }

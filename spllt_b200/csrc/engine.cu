@@ -186,6 +186,20 @@ void Engine::upload_tables() {
       r.end = i;
     }
   }
+  // which launches scatter into the upper tree while other ranks may do the same (multi-GPU phase 0)
+  launch_sys.assign(S.launches.size(), 0);
+  if (S.world > 1)
+    for (size_t i = 0; i < S.launches.size(); ++i) {
+      const Launch& L = S.launches[i];
+      if (L.phase != 0 || (L.kind != L_TILE_S && L.kind != L_TILE_L)) continue;
+      for (i64 k = L.begin; k < L.begin + L.count && !launch_sys[i]; ++k) {
+        const TileTask& t = S.tile_tasks[k];
+        if (t.src < 0) continue;
+        const HNode& nd = S.nodes[t.node];
+        // destination columns = ancestors owning source rows [j0, j0 + nt): sorted, so the last one decides
+        if (S.nodes[S.col2node[S.index[nd.idx_off + t.j0 + t.nt - 1]]].owner < 0) launch_sys[i] = 1;
+      }
+    }
   uploaded = true;
   if (comm_ready) upload_maps();
 }
@@ -281,7 +295,10 @@ void Engine::ensure_solve_buffers(int nrhs) {
 }
 
 void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
-  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos, A->world > 1 ? 1 : 0};
+  // system-scope reductions only where another GPU may add into the same entries at the same time:
+  // phase-0 launches that scatter into the upper tree (peer-owned or shared with peers' scatters)
+  const size_t li = (size_t)(&L - A->launches.data());
+  DevMaps mp{d_qbase, d_qld, d_qrp, d_rowpos, li < launch_sys.size() ? (int)launch_sys[li] : 0};
   switch (L.kind) {
     case L_PANEL: launch_panel(d_panel + L.begin, L.count, arena, d_info, d_counters + A->launches.size(), st); break;
     case L_PUSH: {

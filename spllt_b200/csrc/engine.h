@@ -88,6 +88,7 @@ struct Engine {
   struct StepRange { i64 begin, after_push, end; };
   std::vector<StepRange> step_ranges;   // launch index ranges of the upper-tree steps
   i64 phase0_end = 0;                   // launches [0, phase0_end) belong to phase 0
+  std::vector<char> launch_sys;         // per launch: 1 = its extend-add needs system-scope reductions
 
   void export_handles(void* out128);                       // arena + flag IPC handles (2 x 64 bytes)
   void attach_peers(int rank, int world, const void* all_handles, void* const* same_process);

@@ -87,6 +87,15 @@ __device__ __forceinline__ void cp_commit_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// fire-and-forget reductions (SASS REDG): nothing here needs the old value, and a returning ATOMG
+// keeps a register scoreboard busy until L2 answers (up to microseconds on contended lines)
+__device__ __forceinline__ void red_f64(double* p, double v) {
+  asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_s32(int* p, int v) {
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ int ld_relaxed(const int* p) {
   int v;
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -454,7 +463,7 @@ __device__ __forceinline__ void fwd_below(const PNode& nd, int r0, int nrows, co
     double* dst = a.xw + (i64)myidx * a.nrhs + c.rc0;
 #pragma unroll
     for (int q = 0; q < RC; ++q)
-      if (q < c.nr) atomicAdd(dst + q, -mine[q]);
+      if (q < c.nr) red_f64(dst + q, -mine[q]);
   }
 }
 
@@ -545,7 +554,7 @@ __device__ __forceinline__ void fwd_below_fat(const PNode& nd, int r0, int nrows
       double* dst = a.xw + (i64)myidx * a.nrhs + c.rc0;
 #pragma unroll
       for (int q = 0; q < RC; ++q)
-        if (q < c.nr) atomicAdd(dst + q, -mine[q]);
+        if (q < c.nr) red_f64(dst + q, -mine[q]);
     }
   }
 }
@@ -555,7 +564,7 @@ __device__ __forceinline__ void bump_dests(const int* dest, int count, int* cnt,
   __syncthreads();
   for (int k = threadIdx.x; k < count; k += PT) {
     fence_gpu(mode);
-    atomicAdd(cnt + dest[k], 1);
+    red_s32(cnt + dest[k], 1);
   }
 }
 
@@ -723,8 +732,8 @@ __device__ __forceinline__ void bwd_below(const PNode& nd, int r0, int nrows, co
         double* dst = a.xw + (i64)(nd.sa + col) * a.nrhs + c.rc0;
 #pragma unroll
         for (int q = 0; q < RC; ++q) {
-          if (q < c.nr && col < nd.n) atomicAdd(dst + q, -a0[q]);
-          if (q < c.nr && col + 1 < nd.n) atomicAdd(dst + a.nrhs + q, -a1[q]);
+          if (q < c.nr && col < nd.n) red_f64(dst + q, -a0[q]);
+          if (q < c.nr && col + 1 < nd.n) red_f64(dst + a.nrhs + q, -a1[q]);
           a0[q] = a1[q] = 0.0;
         }
       }
@@ -789,7 +798,7 @@ __global__ void __launch_bounds__(PT, RC == 1 ? PIPE_OCC : 1) k_solve_pipe(const
         __syncthreads();
         if (tk.kind == P_BELOW && tid == 0) {
           fence_gpu(a.mode);
-          atomicAdd(c.cnt + tk.node, 1);
+          red_s32(c.cnt + tk.node, 1);
         }
       }
       if (tk.kind != P_BELOW) bwd_strip<RC>(nd, tk.node, tk.kind == P_DIAG ? tk.r0 : 0, tk.kind == P_DIAG, a, c);
