@@ -406,10 +406,88 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   A.q_ld.assign(nrows, 0);
   A.q_rp.assign(nrows, 0);
   A.rowpos.clear();
+  // Multi-GPU: a node of a subtree this rank owns sends its updates into the upper tree to the
+  // subtree's generated element (local HBM) instead of the upper-tree block columns themselves,
+  // most of which live on other GPUs.  (Scattering every node's update straight into the owners
+  // was measured first: 5.7e8 remote reductions per rank on Poisson 100^3 at 8 GPUs against 3.2e7
+  // entries of the generated element -- NVLink atomics became the bottleneck of the subtree phase.)
+  A.gen.clear();
+  A.gen_doubles = 0;
+  A.gq_base.clear();
+  A.gq_ld.clear();
+  A.gq_bcol.clear();
+  A.gq_rp.clear();
+  std::vector<int> gen_of(nn, -1);          // node -> generated element of its subtree (owned nodes only)
+  if (A.world > 1) {
+    for (int s = nn - 1; s >= 0; --s) {     // parents before children (postorder numbering)
+      const HNode& nd = A.nodes[s];
+      if (nd.owner != A.rank) continue;
+      const int par = nd.parent;
+      if (par >= 0 && A.nodes[par].owner == A.rank) {
+        gen_of[s] = gen_of[par];
+      } else if (nd.m > nd.n) {
+        GenElem g;
+        g.root = s;
+        g.b = nd.m - nd.n;
+        g.off = A.gen_doubles;
+        g.map0 = 0;
+        A.gen_doubles += rup((i64)g.b * g.b, 16);
+        gen_of[s] = (int)A.gen.size();
+        A.gen.push_back(g);
+      }
+    }
+  }
   for (int s = 0; s < nn; ++s) {
     const HNode& nd = A.nodes[s];
     const int* idx = A.index.data() + nd.idx_off;
     int r = nd.n;
+    if (gen_of[s] >= 0) {
+      // rows [r_top, m) belong to the upper tree (pivot order: the upper tree follows every subtree)
+      const GenElem& g = A.gen[gen_of[s]];
+      const HNode& rt = A.nodes[g.root];
+      const int* ridx = A.index.data() + rt.idx_off + rt.n;
+      int r_top = nd.m;
+      for (int q = nd.n; q < nd.m; ++q)
+        if (A.nodes[A.col2node[idx[q]]].owner < 0) { r_top = q; break; }
+      if (r_top < nd.m) {
+        // positions of rows [r_top, m) in the element = in the root's list of rows below (merge)
+        const i64 rp = (i64)A.rowpos.size() - r_top;
+        int pa = 0;
+        for (int q = r_top; q < nd.m; ++q) {
+          while (ridx[pa] != idx[q]) ++pa;
+          A.rowpos.push_back(pa);
+          const i64 gq = nd.row_base + (q - nd.n);
+          A.q_base[gq] = -(1 + g.off + pa);
+          A.q_ld[gq] = g.b;
+          A.q_rp[gq] = rp;
+        }
+      }
+      // the ancestors inside the subtree are handled below, up to r_top
+      const int m_sub = r_top;
+      while (r < m_sub) {
+        int a = A.col2node[idx[r]];
+        const HNode& an = A.nodes[a];
+        int r1 = r;
+        while (r1 < m_sub && idx[r1] <= an.en) ++r1;
+        i64 rp = (i64)A.rowpos.size() - r;
+        const int* aidx = A.index.data() + an.idx_off;
+        int pa = idx[r] - an.sa;
+        // rows [r, m_sub) are rows of a inside the subtree; rows [m_sub, m) are rows of a too (upper
+        // tree), but the product entries (i >= m_sub, j in [r, r1)) belong to a's rows -> still needed
+        for (int q = r; q < nd.m; ++q) {
+          while (aidx[pa] != idx[q]) ++pa;
+          A.rowpos.push_back(pa);
+        }
+        for (int q = r; q < r1; ++q) {
+          i64 gq = nd.row_base + (q - nd.n);
+          A.q_base[gq] = an.off + (idx[q] - an.sa);
+          A.q_ld[gq] = an.ld;
+          A.q_rp[gq] = rp;
+        }
+        r = r1;
+      }
+      continue;
+    }
     while (r < nd.m) {
       int a = A.col2node[idx[r]];
       const HNode& an = A.nodes[a];
@@ -430,6 +508,38 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
         A.q_rp[g] = rp;
       }
       r = r1;
+    }
+  }
+  // where the generated elements land in the upper tree: the maps of the subtree ROOTS' rows below
+  // (element row / column i = root row n + i), used once per factorization by the apply kernel
+  for (GenElem& g : A.gen) {
+    const HNode& nd = A.nodes[g.root];
+    const int* idx = A.index.data() + nd.idx_off + nd.n;
+    g.map0 = (i64)A.gq_base.size();
+    A.gq_base.resize(g.map0 + g.b);
+    A.gq_ld.resize(g.map0 + g.b);
+    A.gq_bcol.resize(g.map0 + g.b);
+    A.gq_rp.resize(g.map0 + g.b);
+    int i = 0;
+    while (i < g.b) {
+      const int a = A.col2node[idx[i]];
+      const HNode& an = A.nodes[a];
+      int i1 = i;
+      while (i1 < g.b && idx[i1] <= an.en) ++i1;
+      const i64 rp = (i64)A.rowpos.size() - i;
+      const int* aidx = A.index.data() + an.idx_off;
+      int pa = idx[i] - an.sa;
+      for (int q = i; q < g.b; ++q) {
+        while (aidx[pa] != idx[q]) ++pa;
+        A.rowpos.push_back(pa);
+      }
+      for (int q = i; q < i1; ++q) {
+        A.gq_base[g.map0 + q] = an.off + (idx[q] - an.sa);
+        A.gq_ld[g.map0 + q] = an.ld;
+        A.gq_bcol[g.map0 + q] = an.bcol0 + (idx[q] - an.sa) / nb;
+        A.gq_rp[g.map0 + q] = rp;
+      }
+      i = i1;
     }
   }
 
@@ -664,22 +774,22 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
             flush_tiles(t, 4);
           }
         }
-        // delivery: first to the rank whose panel chain needs this block column next (the owner
-        // of the node's next block column, or of the ancestor block column its first row below
-        // maps to), then to everybody else -- the owner's NVLink egress is the bottleneck of a
-        // push (rows x w doubles to world - 1 peers), the next chain should not wait for all of it
-        int first = -1;
-        if (ts_.c + 1 < nd.nc) first = A.bcol_owner[g + 1];
-        else if (nd.m > nd.n) {
-          const int piv = A.index[nd.idx_off + nd.n];
-          const int a = A.col2node[piv];
-          first = A.bcol_owner[A.nodes[a].bcol0 + (piv - A.nodes[a].sa) / nb];
+        // delivery: one push per peer, in the order in which the peers need the block column --
+        // the owners of the following steps (cyclic ownership: they are all different).  The owner's
+        // NVLink egress (rows x w doubles per peer) is the bottleneck of a delivery; in this order the
+        // next chain waits for one copy, not for world - 1 of them.
+        {
+          unsigned done = 1u << A.rank;
+          int k = 0;
+          for (size_t t2 = t + 1; t2 < A.top_steps.size() && k < A.world - 1; ++t2) {
+            const int o2 = A.top_steps[t2].owner;
+            if (done >> o2 & 1u) continue;
+            done |= 1u << o2;
+            A.launches.push_back({L_PUSH, t, (i64)g, k++, 1, 8, 0, 1 << o2});
+          }
+          for (int o2 = 0; o2 < A.world; ++o2)      // (the last steps: everybody still needs the factor for the solve)
+            if (!(done >> o2 & 1u)) A.launches.push_back({L_PUSH, t, (i64)g, k++, 1, 8, 0, 1 << o2});
         }
-        const int all = ((1 << A.world) - 1) & ~(1 << A.rank);
-        int m1 = (first >= 0 && first != A.rank) ? (1 << first) : 0;
-        if (getenv("SPLLT_B200_PUSH_ONESHOT")) m1 = 0;
-        if (m1) A.launches.push_back({L_PUSH, t, (i64)g, 0, 1, 8, 0, m1});
-        if (all & ~m1) A.launches.push_back({L_PUSH, t, (i64)g, 1, 1, 8, 0, all & ~m1});
       } else {
         flush_rest(t);
         A.launches.push_back({L_WAIT, t, (i64)g, 1, 1, 9, 0, 0});

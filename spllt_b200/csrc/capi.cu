@@ -758,6 +758,7 @@ int spllt_b200_emulate_ranks_factor(void** fkeeps, int world, const double* d_va
     for (int r = 0; r < world; ++r) {
       E[r]->factor_barrier(1, 2, st);
       E[r]->enqueue_range(0, E[r]->phase0_end, st);
+      E[r]->apply_generated(st);
       E[r]->factor_barrier(2, 1, st);
     }
     for (int r = 0; r < world; ++r) E[r]->factor_barrier(2, 2, st);

@@ -66,7 +66,8 @@ void Engine::upload_tables() {
   CK(cudaMemset(arena, 0, std::max<i64>(S.arena, 1) * sizeof(double)));
   CK(cudaMalloc(&d_flags, (F_BCOL + std::max(S.nbcol, 1)) * sizeof(int)));
   CK(cudaMemset(d_flags, 0, (F_BCOL + std::max(S.nbcol, 1)) * sizeof(int)));
-  CK(cudaMalloc(&d_pushcnt, 2 * std::max(S.nbcol, 1) * sizeof(int)));
+  CK(cudaMalloc(&d_pushcnt, MAX_RANKS * std::max(S.nbcol, 1) * sizeof(int)));
+  if (S.gen_doubles > 0) CK(cudaMalloc(&d_gen, S.gen_doubles * sizeof(double)));   // generated elements of my subtrees
   if (S.world <= 1) {   // single GPU: the "peer set" is this arena
     peers = PeerSet{};
     peers.rank = 0;
@@ -186,20 +187,9 @@ void Engine::upload_tables() {
       r.end = i;
     }
   }
-  // which launches scatter into the upper tree while other ranks may do the same (multi-GPU phase 0)
+  // system-scope reductions: only the apply kernel of the generated elements adds into memory that
+  // other GPUs add into at the same time; every tile launch scatters into this rank's own HBM
   launch_sys.assign(S.launches.size(), 0);
-  if (S.world > 1)
-    for (size_t i = 0; i < S.launches.size(); ++i) {
-      const Launch& L = S.launches[i];
-      if (L.phase != 0 || (L.kind != L_TILE_S && L.kind != L_TILE_L)) continue;
-      for (i64 k = L.begin; k < L.begin + L.count && !launch_sys[i]; ++k) {
-        const TileTask& t = S.tile_tasks[k];
-        if (t.src < 0) continue;
-        const HNode& nd = S.nodes[t.node];
-        // destination columns = ancestors owning source rows [j0, j0 + nt): sorted, so the last one decides
-        if (S.nodes[S.col2node[S.index[nd.idx_off + t.j0 + t.nt - 1]]].owner < 0) launch_sys[i] = 1;
-      }
-    }
   uploaded = true;
   if (comm_ready) upload_maps();
 }
@@ -221,12 +211,33 @@ void Engine::upload_maps() {
         const int a = S.col2node[idx[r]];
         owner = S.bcol_owner[S.nodes[a].bcol0 + (idx[r] - S.nodes[a].sa) / nb];
       }
-      qa[g] = (i64)(uintptr_t)(peers.arena[owner] + S.q_base[g]);
+      if (S.q_base[g] < 0)   // into the generated element of the node's subtree (local)
+        qa[g] = (i64)(uintptr_t)(d_gen + (-S.q_base[g] - 1));
+      else
+        qa[g] = (i64)(uintptr_t)(peers.arena[owner] + S.q_base[g]);
     }
   }
   if (d_qbase) cudaFree(d_qbase);
   d_qbase = upload(qa);
+  // generated elements -> upper tree: absolute destination columns in their owners' arenas
+  if (!S.gen.empty()) {
+    std::vector<i64> ga(S.gq_base.size());
+    for (size_t k = 0; k < ga.size(); ++k)
+      ga[k] = (i64)(uintptr_t)(peers.arena[S.bcol_owner[S.gq_bcol[k]]] + S.gq_base[k]);
+    if (d_gqbase) cudaFree(d_gqbase);
+    d_gqbase = upload(ga);
+    if (!d_gqld) d_gqld = upload(S.gq_ld);
+    if (!d_gqrp) d_gqrp = upload(S.gq_rp);
+  }
   maps_ready = true;
+}
+
+// a9 (spllt_subtree_apply_buffer): the generated elements of this rank's subtrees are added into the
+// upper-tree block columns, wherever they live
+void Engine::apply_generated(cudaStream_t st) {
+  const Analysis& S = *A;
+  for (const GenElem& g : S.gen)
+    launch_apply_gen(d_gen + g.off, g.b, d_gqbase + g.map0, d_gqld + g.map0, d_gqrp + g.map0, d_rowpos, st);
 }
 
 // ---- multi-GPU bootstrap.  export_handles: CUDA IPC handles of this rank's arena and flag block;
@@ -305,7 +316,7 @@ void Engine::launch_one(const Launch& L, cudaStream_t st, bool background) {
       const HNode& nd = A->nodes[A->bcol_node[L.begin]];
       const int r0 = A->bcol_c[L.begin] * A->nb;
       launch_push_bcol(peers, (unsigned)L.deadline, nd.off + (i64)r0 * nd.ld + r0, nd.ld, nd.m - r0,
-                       std::min(A->nb, nd.n - r0), (int)L.begin, d_pushcnt + 2 * L.begin + L.count, st);
+                       std::min(A->nb, nd.n - r0), (int)L.begin, d_pushcnt + MAX_RANKS * L.begin + L.count, st);
       break;
     }
     case L_WAIT: launch_wait_bcol(d_flags, (int)L.begin, st); break;
@@ -333,7 +344,8 @@ void Engine::factor_begin(const double* dval, cudaStream_t st) {
   if (S.world > 1) {
     if (S.own_end > S.own_begin) CK(cudaMemsetAsync(arena + S.own_begin, 0, (S.own_end - S.own_begin) * sizeof(double), st));
     if (S.arena > S.top_begin) CK(cudaMemsetAsync(arena + S.top_begin, 0, (S.arena - S.top_begin) * sizeof(double), st));
-    CK(cudaMemsetAsync(d_pushcnt, 0, 2 * std::max(S.nbcol, 1) * sizeof(int), st));
+    CK(cudaMemsetAsync(d_pushcnt, 0, MAX_RANKS * std::max(S.nbcol, 1) * sizeof(int), st));
+    if (S.gen_doubles > 0) CK(cudaMemsetAsync(d_gen, 0, S.gen_doubles * sizeof(double), st));
   } else {
     CK(cudaMemsetAsync(arena, 0, S.arena * sizeof(double), st));
   }
@@ -429,6 +441,7 @@ void Engine::enqueue_factor(const double* dval, cudaStream_t st) {
   factor_begin(dval, st);
   factor_barrier(1, 0, st);
   enqueue_range(0, phase0_end, st);
+  apply_generated(st);
   factor_barrier(2, 0, st);
   enqueue_range(phase0_end, (i64)S.launches.size(), st);
   factor_end(st);
@@ -484,7 +497,10 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
   for (auto& e : ev0) CK(cudaEventCreate(&e));
   for (size_t i = 0; i < S.launches.size(); ++i) {
     const Launch& L = S.launches[i];
-    if ((i64)i == phase0_end) factor_barrier(2, 0, st);
+    if ((i64)i == phase0_end) {
+      apply_generated(st);
+      factor_barrier(2, 0, st);
+    }
     CK(cudaEventRecord(ev0[i], st));
     if ((int)i == dbg_launch && L.kind == L_PANEL) {
       dbg_count = L.count;
@@ -495,7 +511,10 @@ void Engine::profile_factor(const double* dval, double* ms4, const char* csv) {
     }
     CK(cudaEventRecord(ev[i + 2], st));
   }
-  if (phase0_end == (i64)S.launches.size()) factor_barrier(2, 0, st);
+  if (phase0_end == (i64)S.launches.size()) {
+    apply_generated(st);
+    factor_barrier(2, 0, st);
+  }
   CK(cudaStreamSynchronize(st));
   if (dbg) {
     std::vector<long long> h(dbg_count * 8);
@@ -828,6 +847,14 @@ void Engine::release() {
   ipc_open.clear();
   cudaFree(d_flags);
   cudaFree(d_pushcnt);
+  if (d_gen) cudaFree(d_gen);
+  if (d_gqbase) cudaFree(d_gqbase);
+  if (d_gqld) cudaFree(d_gqld);
+  if (d_gqrp) cudaFree(d_gqrp);
+  d_gen = nullptr;
+  d_gqbase = nullptr;
+  d_gqld = nullptr;
+  d_gqrp = nullptr;
   d_flags = d_pushcnt = nullptr;
   d_qbase = nullptr;
   comm_ready = maps_ready = false;

@@ -83,7 +83,12 @@ struct Engine {
   bool comm_ready = false;        // world == 1, or attach_peers() has run
   bool maps_ready = false;        // q_base (absolute addresses) uploaded
   int* d_flags = nullptr;         // this rank's flag block (F_EPOCH / F_BAR / F_BCOL)
-  int* d_pushcnt = nullptr;       // [nbcol] CTAs of a push that have finished (zeroed per factorization)
+  int* d_pushcnt = nullptr;       // [nbcol][MAX_RANKS] CTAs of a push that have finished (zeroed per factorization)
+  double* d_gen = nullptr;        // generated elements of the subtrees this rank owns (Analysis::gen)
+  i64* d_gqbase = nullptr;        // their destination maps (absolute addresses, owners' arenas)
+  int* d_gqld = nullptr;
+  i64* d_gqrp = nullptr;
+  void apply_generated(cudaStream_t st);
   std::vector<void*> ipc_open;    // mappings to close on release
   struct StepRange { i64 begin, after_push, end; };
   std::vector<StepRange> step_ranges;   // launch index ranges of the upper-tree steps

@@ -1445,6 +1445,26 @@ __global__ void k_rank_barrier(PeerSet ps, int id, int what) {
   }
 }
 
+// a9: spllt_subtree_apply_buffer / spllt_scatter_block (src/spllt_factorization_mod.F90:39-191,
+// src/spllt_kernels_mod.F90:1122-1160).  G: b x b generated element of one subtree (lower triangle,
+// row-major, already negated: the update epilogues accumulated -L L^T into it).  Entry (i, j) goes
+// to column gq_base[j] (absolute address in the OWNER's arena, possibly a peer mapping), row
+// rowpos[gq_rp[j] + i] -- one system-scope reduction per entry, 64 consecutive columns per warp pass.
+__global__ void __launch_bounds__(256) k_apply_gen(const double* __restrict__ G, int b, const i64* __restrict__ gq_base,
+                                                   const int* __restrict__ gq_ld, const i64* __restrict__ gq_rp,
+                                                   const int* __restrict__ rowpos) {
+  const int j = blockIdx.x * 64 + (threadIdx.x & 63);        // column of the element
+  const int i0 = blockIdx.y * 64;                             // 64-row block
+  if (i0 + 63 < blockIdx.x * 64 || j >= b) return;            // block above the diagonal / beyond the edge
+  const i64 base = gq_base[j], rp = gq_rp[j];
+  const int ld = gq_ld[j];
+  for (int i = i0 + (threadIdx.x >> 6); i < min(i0 + 64, b); i += 4) {
+    if (i < j) continue;
+    const double v = G[(i64)i * b + j];
+    if (v != 0.0) red_add_f64<true>(base + 8 * ((i64)rowpos[rp + i] * ld), v);
+  }
+}
+
 // max |a - b| and max |b| over the lower trapezoids of a list of nodes held in two arenas with
 // different layouts (multi-GPU factor against a single-GPU factor): out[0], out[1] as ordered bits
 struct CmpNode {
@@ -1566,6 +1586,12 @@ void launch_push_bcol(const PeerSet& ps, unsigned mask, i64 off, int ld, int row
 void launch_wait_bcol(const int* flags, int bc, cudaStream_t st) { k_wait_bcol<<<1, 1, 0, st>>>(flags, bc); }
 void launch_rank_barrier(const PeerSet& ps, int id, int what, cudaStream_t st) {
   k_rank_barrier<<<1, 32, 0, st>>>(ps, id, what);
+}
+void launch_apply_gen(const double* G, int b, const i64* gq_base, const int* gq_ld, const i64* gq_rp, const int* rowpos,
+                      cudaStream_t st) {
+  if (b <= 0) return;
+  const unsigned nb64 = (unsigned)((b + 63) / 64);
+  k_apply_gen<<<dim3(nb64, nb64), 256, 0, st>>>(G, b, gq_base, gq_ld, gq_rp, rowpos);
 }
 void launch_compare_nodes(const void* nodes, int count, const double* a, const double* b, unsigned long long* out,
                           cudaStream_t st) {

@@ -46,6 +46,9 @@ void launch_push_bcol(const PeerSet& ps, unsigned mask, i64 off, int ld, int row
                       cudaStream_t st);
 void launch_wait_bcol(const int* flags, int bc, cudaStream_t st);
 void launch_rank_barrier(const PeerSet& ps, int id, int what, cudaStream_t st);
+// generated element (b x b, lower triangle) of a subtree -> upper-tree block columns of any rank
+void launch_apply_gen(const double* G, int b, const i64* gq_base, const int* gq_ld, const i64* gq_rp, const int* rowpos,
+                      cudaStream_t st);
 // nodes: device array of {i64 off_a, off_b; int m, n, ld, pad}; out[0] = max |a - b|, out[1] = max |b| (bits)
 void launch_compare_nodes(const void* nodes, int count, const double* a, const double* b, unsigned long long* out,
                           cudaStream_t st);

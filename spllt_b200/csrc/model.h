@@ -84,7 +84,7 @@ struct TileTask {
 // one per upper-tree block column, in the same global order on every rank.
 //   L_PUSH : this rank owns the block column of the step and has just factorized it: copy it into
 //            the arenas of the peers in the mask `deadline` over NVLink and raise its flag there
-//            (begin = global block column, count = 0 / 1: first / second push of the step)
+//            (begin = global block column, count = 0 .. world-2: ordinal of this push of the step)
 //   L_WAIT : another rank owns it: wait for the flag (begin = global block column)
 enum LaunchKind { L_PANEL = 0, L_TILE_S = 1, L_TILE_L = 2, L_PUSH = 3, L_WAIT = 4, L_NKIND = 5 };
 struct Launch {
@@ -97,6 +97,16 @@ struct Launch {
                      // 7 urgent updates of a step (destinations whose turn comes next), 8 push, 9 wait
   int stream;        // 0 = main; 1 = background stream (deferred inter-node updates)
   int deadline;      // background launches: the slot whose panel launch must wait for them
+};
+// Multi-GPU: the generated element of one subtree this rank owns (src/spllt_kernels_mod.F90:780-821
+// `buffer`, size (m - n)^2 of the subtree root): every update of a subtree node into the upper tree is
+// accumulated HERE, in local HBM, and scattered once into the owners of the upper-tree block columns
+// when the subtree is complete (a9: spllt_subtree_apply_buffer / spllt_scatter_block).
+struct GenElem {
+  int root;          // subtree root node
+  int b;             // rows below the root's diagonal block = side of the element
+  i64 off;           // offset (doubles) in the rank's element buffer; entry (i, j), i >= j, at off + i * b + j
+  i64 map0;          // gq_* index of the root's first below-diagonal row
 };
 struct TopStep {     // one upper-tree block column in the global step order
   int node, c;       // node (0-based), local block column
@@ -216,6 +226,14 @@ struct Analysis {
   std::vector<int> q_ld;           //   leading dimension of that dest node
   std::vector<i64> q_rp;           //   rowpos[q_rp[j] + r] = row position of source row r in dest
   std::vector<int> rowpos;
+  // multi-GPU: generated elements of the subtrees this rank owns; q_base < 0 encodes a destination
+  // inside the element buffer (-(1 + offset)); gq_*: where an element's columns / rows land in the
+  // upper tree (same meaning as q_*, indexed from GenElem::map0)
+  std::vector<GenElem> gen;
+  i64 gen_doubles = 0;
+  std::vector<i64> gq_base;        // arena offset of the destination column
+  std::vector<int> gq_ld, gq_bcol; // leading dimension, global block column (-> owner) of the destination
+  std::vector<i64> gq_rp;          // rowpos[gq_rp + i] = row position of element row i in that destination node
   double tile_flops = 0;           // flops issued by the tile kernels (incl. masked halves)
   double tile_flops_algo = 0;      // algorithmic flops of the same tiles (2 kk per entry with i >= j)
 
