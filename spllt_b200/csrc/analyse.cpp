@@ -750,6 +750,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   if (A.world > 1 && A.dist_top) {
     cur_phase = 1;
     const int window = std::max(1, getenv("SPLLT_B200_TOP_WINDOW") ? atoi(getenv("SPLLT_B200_TOP_WINDOW")) : 2);
+    const bool chain_ahead = !getenv("SPLLT_B200_NO_CHAIN_AHEAD");
     std::vector<Region> rest;   // deferred updates of the previous step
     auto flush_rest = [&](int t) {
       if (rest.empty()) return;
@@ -770,8 +771,25 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
           emit_panel(nd, k0, pw);
           A.launches.push_back({L_PANEL, t, p0, (i64)A.panel_tasks.size() - p0, 1, 0, 0, 0});
           if (k0 + pw < r0 + w) {
-            inner_updates(nd, r0, w, k0, pw);
+            // Look-ahead inside the chain: only the NEXT panel's 64 columns must be up to date before
+            // its k_panel; the update of the columns behind them (tag 3) is forked onto a side stream
+            // and runs while the next panel is factorized -- the chain owner's SMs are mostly idle
+            // during a k_panel (one CTA per 128 rows).  Same two-level blocking as inner_updates.
+            const int bend = r0 + w;
+            const int mb0 = r0 + (k0 - r0) / mid_w * mid_w, me = std::min(mb0 + mid_w, bend);
+            const bool inside = k0 + pw < me;
+            const int c0 = inside ? k0 + pw : me, cend = inside ? me : bend;
+            const int ks = inside ? k0 : mb0, kw = inside ? pw : me - mb0;
+            const int cn = std::min(c0 + IB, cend);
+            add_tiles(A, ts, tl, nd, c0, cn, 0, nd.m, ks, kw, -1, tile_l_min);
             flush_tiles(t, 4);
+            if (cn < cend && chain_ahead) {
+              add_tiles(A, ts, tl, nd, cn, cend, 0, nd.m, ks, kw, -1, tile_l_min);
+              flush_tiles(t, 3);
+            } else if (cn < cend) {
+              add_tiles(A, ts, tl, nd, cn, cend, 0, nd.m, ks, kw, -1, tile_l_min);
+              flush_tiles(t, 4);
+            }
           }
         }
         // delivery: one push per peer, in the order in which the peers need the block column --

@@ -60,6 +60,9 @@ void Engine::upload_tables() {
     CK(cudaStreamCreateWithPriority(&bg, cudaStreamNonBlocking, lo));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ahead, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_ahead, cudaEventDisableTiming));
   }
   overlap_tiles = !getenv("SPLLT_B200_NO_OVERLAP");
   CK(cudaMalloc(&arena, std::max<i64>(S.arena, 1) * sizeof(double)));
@@ -395,8 +398,25 @@ void Engine::enqueue_range(i64 first, i64 last, cudaStream_t st) {
     pending.erase(pending.begin(), pending.begin() + lastp + 1);
   };
   cudaEvent_t ev_panel = nullptr;
+  bool ahead_pending = false;   // a tag-3 launch is running on `ahead`: join before the next tile launch / push
+  auto join_ahead = [&]() {
+    if (!ahead_pending) return;
+    CK(cudaStreamWaitEvent(st, ev_ahead, 0));
+    ahead_pending = false;
+  };
   for (i64 i = first; i < last; ++i) {
     const Launch& L = S.launches[i];
+    if (L.tag == 3 && fork && ahead) {   // overlapped with the next panel of the chain
+      if (!ahead_pending) {
+        CK(cudaEventRecord(ev_fork2, st));
+        CK(cudaStreamWaitEvent(ahead, ev_fork2, 0));
+      }
+      launch_one(L, ahead, false);
+      CK(cudaEventRecord(ev_ahead, ahead));
+      ahead_pending = true;
+      continue;
+    }
+    if (L.kind != L_PANEL) join_ahead();
     if (L.stream == 1 && fork && ev_panel) {
       CK(cudaStreamWaitEvent(bg, ev_panel, 0));
       launch_one(L, bg, true);
@@ -428,6 +448,7 @@ void Engine::enqueue_range(i64 first, i64 last, cudaStream_t st) {
     }
     launch_one(L, st, false);
   }
+  join_ahead();
   join_bg(1 << 30);
 }
 
@@ -904,6 +925,12 @@ void Engine::release() {
     bg = nullptr;
     cudaEventDestroy(ev_fork);
     cudaEventDestroy(ev_join);
+    if (ahead) {
+      cudaStreamDestroy(ahead);
+      cudaEventDestroy(ev_fork2);
+      cudaEventDestroy(ev_ahead);
+      ahead = nullptr;
+    }
     side = nullptr;
   }
   uploaded = false;

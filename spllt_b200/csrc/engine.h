@@ -35,6 +35,8 @@ struct Engine {
   size_t ev_used = 0;
   i64 lmap_count = 0;             // A -> L entries this rank assembles
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t ahead = nullptr;   // chain look-ahead: updates that run while the next panel is factorized
+  cudaEvent_t ev_fork2 = nullptr, ev_ahead = nullptr;
   bool overlap_tiles = true;
   int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
 

@@ -93,7 +93,8 @@ struct Launch {
   i64 begin;         // first task in the list of this kind
   i64 count;         // tasks (= CTAs)
   int phase;         // multi-GPU: 0 = subtrees owned by this rank, 1 = upper tree
-  int tag;           // 0 panel, 4 updates on the critical path, 5 deferred updates (previous step),
+  int tag;           // 0 panel, 4 updates on the critical path, 3 updates overlapped with the next panel of a
+                     // chain (side stream, joined before the next tile launch), 5 deferred updates (previous step),
                      // 7 urgent updates of a step (destinations whose turn comes next), 8 push, 9 wait
   int stream;        // 0 = main; 1 = background stream (deferred inter-node updates)
   int deadline;      // background launches: the slot whose panel launch must wait for them

@@ -185,7 +185,7 @@ def test_distributed_programs_replay(world, grid, nb):
                         sb = int(bcol0[tnode] + k0 // nb)
                         assert (k0 + kk - 1) // nb == k0 // nb
                         if sb == d:
-                            assert d == cur_own and tag == 4       # inner update of the running chain
+                            assert d == cur_own and tag in (3, 4)  # inner update of the running chain
                             continue
                         srcs = [sb]
                     else:
