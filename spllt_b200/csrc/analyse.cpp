@@ -633,11 +633,29 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   // date.  Same arithmetic on every entry (right-looking, every update applied before the
   // entry's own panel), 2.2x less traffic, and most of those flops move to K = 256 tiles.
   const int mid_w = std::max(IB, (getenv("SPLLT_B200_MID_BLOCK") ? atoi(getenv("SPLLT_B200_MID_BLOCK")) : 256) / IB * IB);
+  // Look-ahead: only the NEXT panel's 64 columns must be up to date before its k_panel.  The update
+  // of the columns behind them goes to `regions_ahead` (launch tag 3): it is forked onto a side stream
+  // and runs while the next panels are factorized -- near the top of the tree a k_panel launch (one CTA
+  // per 128 rows of one or two supernodes) leaves most SMs idle.  It is joined before the next tile
+  // launch, so the order of the read-modify-write updates of any entry is unchanged.
+  const bool chain_ahead = !getenv("SPLLT_B200_NO_CHAIN_AHEAD");
+  std::vector<Region> regions_ahead;
   auto inner_updates = [&](const HNode& nd, int r0, int w, int k0, int pw) {
     const int bend = r0 + w;
     const int mb0 = r0 + (k0 - r0) / mid_w * mid_w, me = std::min(mb0 + mid_w, bend);
-    if (k0 + pw < me) add_tiles(A, ts, tl, nd, k0 + pw, me, 0, nd.m, k0, pw, -1, tile_l_min);
-    else if (me < bend) add_tiles(A, ts, tl, nd, me, bend, 0, nd.m, mb0, me - mb0, -1, tile_l_min);
+    const bool inside = k0 + pw < me;
+    if (!inside && me >= bend) return;
+    const int c0 = inside ? k0 + pw : me, cend = inside ? me : bend;
+    const int ks = inside ? k0 : mb0, kw = inside ? pw : me - mb0;
+    const int cn = chain_ahead ? std::min(c0 + IB, cend) : cend;
+    add_tiles(A, ts, tl, nd, c0, cn, 0, nd.m, ks, kw, -1, tile_l_min);
+    if (cn < cend) regions_ahead.push_back({&nd, cn, cend, 0, nd.m, ks, kw, -1});
+  };
+  auto flush_ahead = [&](int depth) {
+    if (regions_ahead.empty()) return;
+    regions.insert(regions.end(), regions_ahead.begin(), regions_ahead.end());
+    regions_ahead.clear();
+    flush_tiles(depth, 3);
   };
 
   // ---- phase 0: every node on one GPU; the subtrees this rank owns on several
@@ -722,6 +740,7 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
       if ((i64)A.panel_tasks.size() > p0)
         A.launches.push_back({L_PANEL, d, p0, (i64)A.panel_tasks.size() - p0, phase, 0, 0, 0});
       flush_tiles(d, 4);
+      flush_ahead(d);
       for (const Region& r : excl_regions) {   // one launch per big finishing node, after the shared ones
         emit_tiles(A, tl, r, 128, A.tile_n);
         std::stable_sort(tl.begin(), tl.end(), [](const TileTask& a, const TileTask& b) {
@@ -750,7 +769,6 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   if (A.world > 1 && A.dist_top) {
     cur_phase = 1;
     const int window = std::max(1, getenv("SPLLT_B200_TOP_WINDOW") ? atoi(getenv("SPLLT_B200_TOP_WINDOW")) : 2);
-    const bool chain_ahead = !getenv("SPLLT_B200_NO_CHAIN_AHEAD");
     std::vector<Region> rest;   // deferred updates of the previous step
     auto flush_rest = [&](int t) {
       if (rest.empty()) return;
@@ -771,25 +789,9 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
           emit_panel(nd, k0, pw);
           A.launches.push_back({L_PANEL, t, p0, (i64)A.panel_tasks.size() - p0, 1, 0, 0, 0});
           if (k0 + pw < r0 + w) {
-            // Look-ahead inside the chain: only the NEXT panel's 64 columns must be up to date before
-            // its k_panel; the update of the columns behind them (tag 3) is forked onto a side stream
-            // and runs while the next panel is factorized -- the chain owner's SMs are mostly idle
-            // during a k_panel (one CTA per 128 rows).  Same two-level blocking as inner_updates.
-            const int bend = r0 + w;
-            const int mb0 = r0 + (k0 - r0) / mid_w * mid_w, me = std::min(mb0 + mid_w, bend);
-            const bool inside = k0 + pw < me;
-            const int c0 = inside ? k0 + pw : me, cend = inside ? me : bend;
-            const int ks = inside ? k0 : mb0, kw = inside ? pw : me - mb0;
-            const int cn = std::min(c0 + IB, cend);
-            add_tiles(A, ts, tl, nd, c0, cn, 0, nd.m, ks, kw, -1, tile_l_min);
+            inner_updates(nd, r0, w, k0, pw);
             flush_tiles(t, 4);
-            if (cn < cend && chain_ahead) {
-              add_tiles(A, ts, tl, nd, cn, cend, 0, nd.m, ks, kw, -1, tile_l_min);
-              flush_tiles(t, 3);
-            } else if (cn < cend) {
-              add_tiles(A, ts, tl, nd, cn, cend, 0, nd.m, ks, kw, -1, tile_l_min);
-              flush_tiles(t, 4);
-            }
+            flush_ahead(t);
           }
         }
         // delivery: one push per peer, in the order in which the peers need the block column --

@@ -61,6 +61,9 @@ void Engine::upload_tables() {
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ahead, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&comm, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork3, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_ahead, cudaEventDisableTiming));
   }
@@ -398,22 +401,48 @@ void Engine::enqueue_range(i64 first, i64 last, cudaStream_t st) {
     pending.erase(pending.begin(), pending.begin() + lastp + 1);
   };
   cudaEvent_t ev_panel = nullptr;
-  bool ahead_pending = false;   // a tag-3 launch is running on `ahead`: join before the next tile launch / push
+  // Look-ahead (tag 3): updates that may run while the NEXT panel launch is executing.  They are
+  // held back until that panel launch has been issued -- issued first, they would occupy every SM
+  // (persistent tile kernel) and the panel would queue behind them -- then forked onto `ahead`, and
+  // joined before the next tile launch / push of the main stream.
+  bool ahead_pending = false;
+  std::vector<const Launch*> stash;
+  auto flush_stash = [&]() {
+    if (stash.empty()) return;
+    CK(cudaStreamWaitEvent(ahead, ev_fork2, 0));
+    for (const Launch* q : stash) launch_one(*q, ahead, false);
+    stash.clear();
+    CK(cudaEventRecord(ev_ahead, ahead));
+    ahead_pending = true;
+  };
   auto join_ahead = [&]() {
+    flush_stash();
     if (!ahead_pending) return;
     CK(cudaStreamWaitEvent(st, ev_ahead, 0));
     ahead_pending = false;
   };
+  // Experiment (opt-in, SPLLT_B200_PUSH_ASYNC=1): deliveries (L_PUSH) on their own stream, so that
+  // the owner's main stream does not stand behind world - 1 NVLink copies.  Measured SLOWER on Poisson
+  // 100^3 at 4 GPUs (78.9 vs 73.9 ms): the copy CTAs take SM slots from the persistent tile kernels.
+  const bool push_async = fork && comm != nullptr && getenv("SPLLT_B200_PUSH_ASYNC");
+  bool comm_pending = false;
+  int comm_step = -1;
   for (i64 i = first; i < last; ++i) {
     const Launch& L = S.launches[i];
-    if (L.tag == 3 && fork && ahead) {   // overlapped with the next panel of the chain
-      if (!ahead_pending) {
-        CK(cudaEventRecord(ev_fork2, st));
-        CK(cudaStreamWaitEvent(ahead, ev_fork2, 0));
+    if (L.kind == L_PUSH && push_async) {
+      if (comm_step != L.depth) {       // first delivery of this step: after everything of the chain
+        join_ahead();
+        CK(cudaEventRecord(ev_fork3, st));
+        CK(cudaStreamWaitEvent(comm, ev_fork3, 0));
+        comm_step = L.depth;
       }
-      launch_one(L, ahead, false);
-      CK(cudaEventRecord(ev_ahead, ahead));
-      ahead_pending = true;
+      launch_one(L, comm, false);
+      comm_pending = true;
+      continue;
+    }
+    if (L.tag == 3 && fork && ahead) {
+      if (stash.empty()) CK(cudaEventRecord(ev_fork2, st));   // depends on everything issued so far
+      stash.push_back(&L);
       continue;
     }
     if (L.kind != L_PANEL) join_ahead();
@@ -428,6 +457,7 @@ void Engine::enqueue_range(i64 first, i64 last, cudaStream_t st) {
     if (L.kind == L_PANEL) {
       join_bg(L.depth);
       launch_one(L, st, false);
+      flush_stash();
       if (fork && L.phase == 0) {
         ev_panel = next_event();
         CK(cudaEventRecord(ev_panel, st));
@@ -449,6 +479,10 @@ void Engine::enqueue_range(i64 first, i64 last, cudaStream_t st) {
     launch_one(L, st, false);
   }
   join_ahead();
+  if (comm_pending) {
+    CK(cudaEventRecord(ev_comm, comm));
+    CK(cudaStreamWaitEvent(st, ev_comm, 0));
+  }
   join_bg(1 << 30);
 }
 
@@ -925,6 +959,12 @@ void Engine::release() {
     bg = nullptr;
     cudaEventDestroy(ev_fork);
     cudaEventDestroy(ev_join);
+    if (comm) {
+      cudaStreamDestroy(comm);
+      cudaEventDestroy(ev_fork3);
+      cudaEventDestroy(ev_comm);
+      comm = nullptr;
+    }
     if (ahead) {
       cudaStreamDestroy(ahead);
       cudaEventDestroy(ev_fork2);

@@ -37,6 +37,8 @@ struct Engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t ahead = nullptr;   // chain look-ahead: updates that run while the next panel is factorized
   cudaEvent_t ev_fork2 = nullptr, ev_ahead = nullptr;
+  cudaStream_t comm = nullptr;    // deliveries of finished block columns to the peers (multi-GPU)
+  cudaEvent_t ev_fork3 = nullptr, ev_comm = nullptr;
   bool overlap_tiles = true;
   int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
 
