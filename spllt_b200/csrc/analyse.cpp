@@ -871,6 +871,11 @@ void partition_tree(Analysis& A, int rank, int world) {
     auto by_weight = [&](int a, int b) { return A.weight[a] > A.weight[b] || (A.weight[a] == A.weight[b] && a < b); };
     std::vector<i64> load(world);
     std::vector<int> where;
+    // SPLLT_B200_SUBTREES_PER_RANK = k: keep splitting until every rank gets at least k subtrees
+    // (smaller subtrees, more -- and more parallel -- work in the upper tree); SPLLT_B200_BALANCE = the
+    // accepted max / mean load of the subtree phase
+    const int min_sub = std::max(1, getenv("SPLLT_B200_SUBTREES_PER_RANK") ? atoi(getenv("SPLLT_B200_SUBTREES_PER_RANK")) : 1);
+    const double tol = getenv("SPLLT_B200_BALANCE") ? atof(getenv("SPLLT_B200_BALANCE")) : 1.10;
     for (int iter = 0; iter < nn; ++iter) {
       std::sort(cand.begin(), cand.end(), by_weight);
       std::fill(load.begin(), load.end(), 0);
@@ -883,7 +888,7 @@ void partition_tree(Analysis& A, int rank, int world) {
         total += A.weight[cand[k]];
       }
       i64 mx = *std::max_element(load.begin(), load.end());
-      bool balanced = (int)cand.size() >= world && (double)mx * world <= 1.10 * (double)total;
+      bool balanced = (int)cand.size() >= min_sub * world && (double)mx * world <= tol * (double)total;
       if (balanced || cand.empty() || child[cand[0]].empty()) break;
       int top = cand[0];   // heaviest: split it
       cand.erase(cand.begin());
