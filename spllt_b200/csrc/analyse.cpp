@@ -1005,6 +1005,8 @@ static void build_pipe_schedule(Analysis& A) {
   const i64 level_tasks = getenv("SPLLT_B200_PIPE_LEVEL_TASKS") ? atoi(getenv("SPLLT_B200_PIPE_LEVEL_TASKS")) : PIPE_LEVEL_TASKS;
   const i64 task_bytes = getenv("SPLLT_B200_PIPE_TASK_KB") ? 1024 * (i64)atoi(getenv("SPLLT_B200_PIPE_TASK_KB")) : PIPE_TASK_BYTES;
   auto is_small = [&](const HNode& nd) { return nd.n <= PS && nd.m - nd.n <= PIPE_SMALL_ROWS; };
+  const int crit_rows = std::max(8, getenv("SPLLT_B200_PIPE_CRIT_ROWS") ? atoi(getenv("SPLLT_B200_PIPE_CRIT_ROWS")) / 8 * 8 : PS);
+  const int crit_np = getenv("SPLLT_B200_PIPE_CRIT_NP") ? atoi(getenv("SPLLT_B200_PIPE_CRIT_NP")) : 3;
   for (int list = 0; list < (multi ? 2 : 1); ++list) {
     std::vector<PTask>& TF = list == 0 ? A.ptasks_f : A.ptasks_ft;
     std::vector<PTask>& TB = list == 0 ? A.ptasks_b : A.ptasks_bt;
@@ -1069,7 +1071,12 @@ static void build_pipe_schedule(Analysis& A) {
         while (crit_end < nd.m && idx[crit_end] <= pend) ++crit_end;
       }
       for (int r = nd.n; r < nd.m;) {
-        const int rows = std::min(r < crit_end ? PS : chunk, nd.m - r);
+        // Experiment (SPLLT_B200_PIPE_CRIT_ROWS < 64): backward, the node's first 64 rows below map to
+        // the parent's LOWEST strips, the last ones to be published; cut into smaller tasks that chunk
+        // is streamed by several CTAs at once.  Measured: no effect (Poisson 64^3 2.09 vs 2.06 ms,
+        // 100^3 9.54 vs 9.65 ms) -- the default keeps 64-row tasks.
+        int rows = std::min(r < crit_end ? PS : chunk, nd.m - r);
+        if (r < nd.n + PS && A.pnodes[s].np >= crit_np) rows = std::min(rows, std::min(crit_rows, nd.n + PS - r));
         PTask t{s, P_BELOW, r, rows, 0, 0, {0, 0}};
         dests(s, r, r + t.nrows, &t.dest_begin, &t.dest_count);
         TF.push_back(t);
