@@ -58,7 +58,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SPLLT_BENCH_WORKLOAD", HEADLINE), choices=sorted(WORKLOADS))
-    ap.add_argument("--nrhs", type=int, default=1)
+    ap.add_argument("--nrhs", default="1", help="right-hand sides of the timed solve; a comma list times several "
+                                                "(the first is the headline, the others go to `solve_more`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 64^3 / 80^3 side measurements")
     return ap.parse_args()
@@ -355,6 +356,8 @@ class Bench:
 
 def main():
     args = parse()
+    nrhs_list = [int(x) for x in str(args.nrhs).split(",")]
+    args.nrhs = nrhs_list[0]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -415,6 +418,10 @@ def main():
             solve["traffic"] = tr
             if tr.get("workload") == args.workload:
                 roofline_solve["traffic"] = tr.get("dram_bytes_read", 0) + tr.get("dram_bytes_write", 0)
+    solve_more = []
+    for nr in nrhs_list[1:]:
+        rep, _ = B.solve_report(solver, mat, nr, 3)
+        solve_more.append(rep)
     parity = {"scaled_backward_error_max": solve["scaled_backward_error_max"], "rhs_ok": solve["rhs_ok"],
               "nrhs": args.nrhs, "tol": 1e-14, "forward_error_max": solve["forward_error_max"],
               "pivot_flag": int(pivot)}
@@ -497,7 +504,7 @@ def main():
             "factor_seconds": ms / 1e3, "analyse_seconds_host": t_analyse,
             "clocks": clk, "e2e": e2e, "gpu_launches": None,
             "roofline": roofline, "roofline_solve": roofline_solve, "cpu_baseline": cpu, "solve": solve,
-            "parity": parity, "extra": extra,
+            "solve_more": solve_more or None, "parity": parity, "extra": extra,
         }
         out["config"].update(cfg_more)
         out["gpu_launches"] = launches_per_factor * args.steps

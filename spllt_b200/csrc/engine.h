@@ -40,7 +40,6 @@ struct Engine {
   cudaStream_t comm = nullptr;    // deliveries of finished block columns to the peers (multi-GPU)
   cudaEvent_t ev_fork3 = nullptr, ev_comm = nullptr;
   bool overlap_tiles = true;
-  int split_depth = 1 << 30;  // multi-GPU: depths >= split belong to the shared top of the tree
 
   double* arena = nullptr;
   i64* d_lmap_dst = nullptr;

@@ -1,9 +1,11 @@
 """Multi-rank check, launched by torchrun (one rank per GPU; backend nccl) or, with
 SPLLT_DIST_CPU=1, on CPU with backend gloo (host logic only).
 
-GPU mode: every rank runs the distributed factorization (subtree mapping + all-reduce of the
-upper tree) and a plain single-GPU factorization of the same matrix, and compares the factor
-entries of every block column it holds (its own subtrees + the shared upper tree).
+GPU mode: every rank runs the distributed factorization (subtree mapping, generated elements
+scattered into the owners' HBM over peer-mapped memory, upper tree distributed by block column)
+and a plain single-GPU factorization of the same matrix, and compares the factor entries of every
+block column it holds (its own subtrees + the upper tree); then the distributed solve and the
+reporting of a non-positive pivot on every rank.
 CPU mode: the ranks exchange their partition tables over gloo and check that they agree, that
 every pruned subtree has exactly one owner and that the per-rank work lists cover every block
 column exactly once.

@@ -111,3 +111,30 @@ def test_empty_matrix_and_unsorted_rows():
     s1.analyse(n, ptr, row)
     s2.analyse(n, ptr, row2)
     assert np.array_equal(s1.order, s2.order) and np.array_equal(s1.blocks(), s2.blocks())
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_numeric_call_without_gpu_fails_loudly_not_fatally():
+    """No CPU fallback: on a machine without a CUDA device every numeric entry point prints the reason
+    and returns SPLLT_ERROR_UNKNOWN (-99) in info%flag -- it must neither compute anything nor abort
+    the caller's process (the reference's error contract, src/spllt_data_mod.F90:31-35)."""
+    import pytest
+    if not _no_gpu():
+        pytest.skip("a CUDA device is present")
+    n, ptr, row, val = M.poisson2d(6)
+    s = sp.SpLLT(nb=8)
+    assert s.analyse(n, ptr, row) == 0           # host only
+    assert s.factor(val) == -99                   # spllt_factor: needs the device
+    x = np.ones(n)
+    assert s.solve(x, 0) == -99 and np.all(x == 1.0)
+    s.wait()                                      # must not crash either
+    # multi-GPU bootstrap without a device: reported through the return code
+    buf = (C.c_char * 128)()
+    assert s.L.spllt_b200_comm_export(s.fkeep, buf) == -99
