@@ -627,11 +627,12 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
   // a3 inside a block column, TWO-LEVEL blocking.  Updating every remaining column of the block
   // column after each 64-column panel (K = 64) makes the block column pass through HBM
   // w / 128 times (11x read-modify-write amplification at w = 768) in tiles that do 1 MFLOP per
-  // 128 KB moved -- measured 8 TF/s, 30 % of a Poisson 100^3 factorization for 12 % of its flops.
-  // Instead the panel only updates the rest of its MID-BLOCK (mid_w = 256 columns); when a
-  // mid-block is complete, ONE K = mid_w update brings the block column's later columns up to
-  // date.  Same arithmetic on every entry (right-looking, every update applied before the
+  // 128 KB moved.  Instead the panel only updates the rest of its MID-BLOCK (mid_w = 256 columns);
+  // when a mid-block is complete, ONE K = mid_w update brings the block column's later columns up
+  // to date.  Same arithmetic on every entry (right-looking, every update applied before the
   // entry's own panel), 2.2x less traffic, and most of those flops move to K = 256 tiles.
+  // (Measured on one GPU: 0.5 % -- the K = 64 tiles hide behind the other supernodes' tiles of the
+  // same launch; it matters for a chain that runs alone.)
   const int mid_w = std::max(IB, (getenv("SPLLT_B200_MID_BLOCK") ? atoi(getenv("SPLLT_B200_MID_BLOCK")) : 256) / IB * IB);
   // Look-ahead: only the NEXT panel's 64 columns must be up to date before its k_panel.  The update
   // of the columns behind them goes to `regions_ahead` (launch tag 3): it is forked onto a side stream

@@ -87,3 +87,22 @@ def test_nb_default_when_nonpositive():
     s = sp.SpLLT(nb=0)
     s.analyse(n, ptr, row)
     assert np.all(s.nodes()[:, 5] == 256)   # nb_default, src/spllt_data_mod.F90:39
+
+
+def test_oracle_side_symbolic_front_end_matches_product():
+    """bench.py's CPU arm takes order / sptr / sparent / rptr / rlist from oracle/libssids_standin.so (the
+    SSIDS stand-in compiled into its own shared object so that the arm never loads the product): same
+    tables as the product's spllt_analyse, bit for bit."""
+    import numpy as np
+    import spllt_b200 as sp
+    from spllt_b200 import matrices as M
+    from oracle import oracle as O
+    for mk, nb in ((lambda: M.poisson3d(14), 32), (lambda: M.elasticity3d(5), 24), (lambda: M.poisson2d(40), 16)):
+        n, ptr, row, val = mk()
+        order, sptr, sparent, rptr, rlist = O.symbolic(n, ptr, row, nemin=32)
+        s = sp.SpLLT(nb=nb)
+        assert s.analyse(n, ptr, row) == 0
+        a = s.symbolic()
+        assert np.array_equal(order, s.order[:n])
+        for x, y in zip((sptr, sparent, rptr, rlist), a):
+            assert np.array_equal(x, y)
