@@ -79,6 +79,15 @@ def make_matrix(workload):
     return getattr(M, gen)(*a), nb, desc
 
 
+L2_NOTE = "working set (factor) far above the 126 MB L2, no flush needed"
+
+
+def workload_config(desc, n, nnz_lower, nnz_L, flops, nb):
+    """`config` of the JSON line -- identical in both arms (same keys, same values)."""
+    return {"workload": desc + ", METIS nested dissection, nemin=32", "n": int(n), "nnz_lower": int(nnz_lower),
+            "nnz_L": int(nnz_L), "flops_per_step": int(flops), "nb": int(nb), "l2": L2_NOTE}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,6 +167,10 @@ class CpuReference:
         self.small = self.o.small()
         self.nn = nn
         self.total = float(self.cum[-1]) if nn else 0.0
+        self.flops_int = int(w[-1])                      # akeep%weight(nnodes+1): the factorization's flop count
+        ncol = np.diff(np.asarray(sptr)).astype(np.int64)
+        mrow = np.diff(np.asarray(rptr)).astype(np.int64)
+        self.nnz_L = int(np.sum(ncol * mrow - ncol * (ncol - 1) // 2))
 
     def prefix_for(self, frac):
         """last node of the smallest postorder prefix holding >= frac of the flops that does not
@@ -210,9 +223,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "factor_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc + ", METIS nested dissection, nemin=32", "flops_per_step": int(fl),
-                   "flops_full_factorization": int(ref.total)},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        # same `config` as the GPU arm; the metric is a rate, the step of THIS arm is the bounded sample below
+        "config": workload_config(desc, mat[0], mat[3].size, ref.nnz_L, ref.flops_int, nb),
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample,
+                         "sample_flops_per_step": int(fl)},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -498,15 +512,13 @@ def main():
             "metric": "factor_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc + ", METIS nested dissection, nemin=32", "n": n, "nnz_lower": int(val.size),
-                       "flops_per_step": int(flops), "nb": nb,
-                       "l2": "working set (factor) far above the 126 MB L2, no flush needed"},
+            "config": workload_config(desc, n, val.size, cfg_more["nnz_L"], flops, nb),
+            "multi_gpu": cfg_more["multi_gpu"], "factor_gb": cfg_more["factor_gb"],
             "factor_seconds": ms / 1e3, "analyse_seconds_host": t_analyse,
             "clocks": clk, "e2e": e2e, "gpu_launches": None,
             "roofline": roofline, "roofline_solve": roofline_solve, "cpu_baseline": cpu, "solve": solve,
             "solve_more": solve_more or None, "parity": parity, "extra": extra,
         }
-        out["config"].update(cfg_more)
         out["gpu_launches"] = launches_per_factor * args.steps
         print(json.dumps(out), flush=True)
     if world > 1:
