@@ -115,9 +115,9 @@ double spllt_b200_peak_probe(int kind, int iters, void *stream);
  * Subtrees of the assembly tree are mapped to ranks by proportional mapping; the upper tree is
  * distributed by block column (owner computes) and walked in the same step order on every rank.
  * Every rank maps every peer's factor arena (CUDA IPC): a subtree's contributions into the upper
- * tree are scattered straight into the owning rank's HBM by the update kernel's epilogue
- * (RED.ADD.F64 on peer addresses -- spllt_subtree_apply_buffer / spllt_scatter_block of the
- * reference, src/spllt_factorization_mod.F90:39-191, without the generated-element buffer), and a
+ * tree are accumulated in its generated element in local HBM (src/spllt_kernels_mod.F90:780-821) and
+ * scattered once into the owning ranks' HBM by an apply kernel (RED.ADD.F64 on peer addresses --
+ * spllt_subtree_apply_buffer / spllt_scatter_block, src/spllt_factorization_mod.F90:39-191), and a
  * finished upper-tree block column is copied into the peers' arenas by its owner's SMs and
  * announced by a flag.  Usage on every rank r of `world`:
  *   spllt_analyse(...);  spllt_b200_partition(akeep, fkeep, r, world);

@@ -17,8 +17,12 @@ for _ in range(5): s.factor_dev(d.data_ptr())
 b.record(); torch.cuda.synchronize()
 print("%.3f ms" % (a.elapsed_time(b) / 5))
 '''
-for env in ({}, {"SPLLT_B200_NO_CHAIN_AHEAD": "1"}, {"SPLLT_B200_GRAPH": "0"}, {"SPLLT_B200_GRAPH": "0", "SPLLT_B200_NO_CHAIN_AHEAD": "1"},
-            {"SPLLT_B200_NO_OVERLAP": "1"}, {"SPLLT_B200_MID_BLOCK": "128"}, {"SPLLT_B200_MID_BLOCK": "192"}, {"SPLLT_B200_MID_BLOCK": "768"}):
+ENVS = [{}, {"SPLLT_B200_NO_CHAIN_AHEAD": "1"}, {"SPLLT_B200_GRAPH": "0"}, {"SPLLT_B200_NO_OVERLAP": "1"},
+        {"SPLLT_B200_MID_BLOCK": "128"}, {"SPLLT_B200_MID_BLOCK": "768"}]
+if len(sys.argv) > 2 and sys.argv[2] == "tiles":
+    ENVS = [{}, {"SPLLT_B200_TILE_WAVE": "64"}, {"SPLLT_B200_TILE_WAVE": "296"}, {"SPLLT_B200_TILE_WAVE": "592"},
+            {"SPLLT_B200_TILE_L_MIN": "64"}, {"SPLLT_B200_TILE_L_MIN": "256"}, {"SPLLT_B200_TILE_L_MIN": "64", "SPLLT_B200_TILE_WAVE": "64"}]
+for env in ENVS:
     e = dict(os.environ); e.update(env)
     r = subprocess.run([sys.executable, "-c", code, wl], env=e, capture_output=True, text=True)
     print(wl, env, r.stdout.strip(), r.stderr.strip()[-200:], flush=True)

@@ -852,9 +852,9 @@ void build_factor_schedule(Analysis& A, int tile_l_min) {
 // candidate subtree is repeatedly split -- its root joins the shared upper tree, its children
 // become candidates -- until the subtrees can be dealt to the ranks (largest first onto the
 // least loaded rank) within 10 % of perfect balance.  The upper tree is distributed by block
-// column (see below); contributions of a subtree into it are scattered straight into the owning
-// rank's arena over NVLink (peer-mapped q_base addresses) -- the generated element of
-// src/spllt_factorization_mod.F90:224-237 never exists as a buffer.  (The reference's pruning,
+// column (see below); a subtree's contributions into it are accumulated in the subtree's generated
+// element (src/spllt_factorization_mod.F90:224-237) and scattered into the owning ranks' arenas over
+// NVLink when the subtree is complete (build_factor_schedule, Engine::apply_generated).  (The reference's pruning,
 // src/spllt_analyse_mod.F90:806-987, plays the mapping role for CPU workers but aims at many small
 // subtrees: with nth = 8 it leaves 81 % of the flops of a 64^3 Poisson problem in the upper tree.)
 void partition_tree(Analysis& A, int rank, int world) {

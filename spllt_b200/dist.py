@@ -9,10 +9,12 @@ calls the same entry points as on one GPU.
 
 Factorization (spllt_b200/csrc/analyse.cpp partition_tree / build_factor_schedule, engine.cu):
   * subtrees of the assembly tree are dealt to the ranks by proportional mapping; each rank
-    factorizes its subtrees in its own HBM; their contributions into the upper tree are scattered
-    straight into the OWNING rank's arena by the update kernel's epilogue (RED.ADD.F64 on
-    peer-mapped addresses over NVLink) -- the reference's generated element
-    (src/spllt_factorization_mod.F90:224-237) never exists as a buffer, nothing is all-reduced;
+    factorizes its subtrees in its own HBM and accumulates their contributions into the upper tree
+    in one generated element per subtree (local HBM; the reference's subtree `buffer`,
+    src/spllt_kernels_mod.F90:780-821); when a subtree is complete one kernel scatters the element
+    straight into the arenas of the ranks that own the destination block columns (RED.ADD.F64 on
+    peer-mapped addresses over NVLink: spllt_subtree_apply_buffer,
+    src/spllt_factorization_mod.F90:39-191) -- nothing is all-reduced;
   * the upper tree is distributed by block column and walked in the same step order on every rank:
     the owner of a step factorizes the block column (panel chain), copies it into every peer's
     arena and raises its flag there; every rank applies it to the destination block columns it owns,
@@ -202,6 +204,6 @@ class DistSpLLT:
         nsteps = int(s.L.spllt_b200_num_top_steps(s.akeep))
         return ("subtree->GPU proportional mapping (%d subtrees; rank %d subtree share %.1f%% of flops); upper tree "
                 "(%.0f%% of flops) distributed by block column, owner computes, %d steps with static look-ahead; "
-                "subtree contributions scattered into the owner's HBM by peer RED.ADD.F64, finished block columns "
-                "pushed into the peers' arenas (CUDA IPC mappings over NVLink), no all-reduce"
+                "generated elements of the subtrees scattered into the owners' HBM by peer RED.ADD.F64, finished "
+                "block columns pushed into the peers' arenas (CUDA IPC mappings over NVLink), no all-reduce"
                 % (nsub, self.rank, 100 * mine / tot, 100 * top / tot, nsteps))
