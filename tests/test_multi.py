@@ -40,7 +40,8 @@ def test_distributed_factor_peer_memory(grid, nb):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,mk,nb", [(2, ("poisson3d", 20), 64), (4, ("poisson3d", 24), 64), (8, ("poisson3d", 28), 32),
-                                         (3, ("elasticity3d", 8), 96), (4, ("poisson3d", 40), 256)])
+                                         (3, ("elasticity3d", 8), 96), (4, ("poisson3d", 40), 256),
+                                         (8, ("poisson3d", 6), 8), (2, ("poisson3d", 3), 4)])   # ranks without work / no upper tree
 def test_distributed_factor_emulated_on_one_gpu(world, mk, nb):
     """The multi-GPU factorization with `world` ranks EMULATED on one GPU (one process, one stream, the
     same per-rank programs / kernels / peer addressing, enqueued in an order in which no kernel waits
@@ -73,7 +74,11 @@ def test_distributed_factor_emulated_on_one_gpu(world, mk, nb):
     for r, e in enumerate(engines):
         assert e.pivot_flag() == 0
         assert L.spllt_b200_compare_factor(e.akeep, e.fkeep, ref.akeep, ref.fkeep, out.ctypes.data_as(C.POINTER(C.c_double))) == 0
-        assert out[1] > 0 and out[0] <= 1e-12 * out[1], (r, out)
+        owners = [L.spllt_b200_node_owner(e.akeep, k + 1) for k in range(e.nnodes)]
+        if any(o == r or o < 0 for o in owners):
+            assert out[1] > 0 and out[0] <= 1e-12 * out[1], (r, out)
+        else:                                   # a rank without any node (fewer subtrees than ranks)
+            assert out[0] == 0 and out[1] == 0
     # (the multi-rank solve needs NCCL all-reduces between its phases: it runs in dist_check.py on >= 2 GPUs)
 
 
@@ -104,7 +109,7 @@ def _rank_tables(mat, nb, rank, world):
     return s, rec[:nrec], tt[:nt], steps[:ns], own[:s.nbcol], float(L.spllt_b200_tile_flops_algo(s.akeep))
 
 
-@pytest.mark.parametrize("world,grid,nb", [(2, 14, 32), (3, 16, 48), (4, 18, 64), (8, 20, 32)])
+@pytest.mark.parametrize("world,grid,nb", [(2, 14, 32), (3, 16, 48), (4, 18, 64), (8, 20, 32), (8, 6, 8), (5, 7, 16), (2, 3, 4)])
 def test_distributed_programs_replay(world, grid, nb):
     import numpy as np
     from spllt_b200 import matrices as M
@@ -123,7 +128,7 @@ def test_distributed_programs_replay(world, grid, nb):
     # the steps and the ownership table are identical on every rank; owners are dealt cyclically
     for r in range(1, world):
         assert np.array_equal(ranks[r][3], steps) and np.array_equal(ranks[r][4], own)
-    assert len(steps) > 0
+    assert len(steps) > 0 or grid <= 3        # (a single supernode: one rank owns everything, no upper tree)
     step_of = {}
     for t, (node, c, o, slot) in enumerate(steps):
         assert node_owner[node] == -1 and o == t % world and own[bcol0[node] + c] == o
