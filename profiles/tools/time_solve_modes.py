@@ -25,7 +25,9 @@ pr = s.profile_solve(dx[0].data_ptr(), 1)
 print("%.3f ms  (fwd %.3f bwd %.3f)  bwd err %.1e ok %d" % (a.elapsed_time(e) / 10, pr["fwd_pipe"], pr["bwd_pipe"], err.max(), ok))
 '''
 ENVS = [{}, {"SPLLT_B200_PIPE_CRIT_ROWS": "16"}, {"SPLLT_B200_PIPE_CRIT_ROWS": "8"}]
-if len(sys.argv) > 2 and sys.argv[2] == "early":
+if len(sys.argv) > 2 and sys.argv[2] == "est":
+    ENVS = [{"SPLLT_B200_PIPE_ORDER_EST": "1"}]
+elif len(sys.argv) > 2 and sys.argv[2] == "early":
     ENVS = [{}, {"SPLLT_B200_PIPE_BWD_EARLY": "1"}]
 elif len(sys.argv) > 2 and sys.argv[2] == "knobs":
     ENVS = [{}, {"SPLLT_B200_PIPE_LEVEL_TASKS": "256"}, {"SPLLT_B200_PIPE_LEVEL_TASKS": "1024"}, {"SPLLT_B200_PIPE_TASK_KB": "32"},

@@ -1102,6 +1102,79 @@ static void build_pipe_schedule(Analysis& A) {
       }
       for (int i = A.pnodes[s].np - 1; i >= 0; --i) TB.push_back(PTask{s, P_DIAG, i, 0, 0, 0, {0, 0}});
     }
+    // EARLIEST-START ORDER (default on one GPU; SPLLT_B200_PIPE_ORDER_EST=0 / 1 forces it off / on): both
+    // lists are sorted by a modelled earliest start time of every task -- the longest path through its
+    // dependencies with rough task costs (2.3 us per strip, hand-off + bytes at 25 GB/s per below task).
+    // CTAs claim tasks in list order, so this is list scheduling: a task is claimed about when its
+    // inputs exist, and the slots are not held by tasks that poll while ready work sits further down
+    // the list (with the (depth, node) order the trace showed 43 % of the CTA-time of a backward sweep
+    // in polling below tasks).  The order stays topological: in the model every dependency ends before
+    // its dependant starts (tests/test_pipe_schedule.py replays and executes the lists).  Measured:
+    // Poisson 100^3 solve 9.6 -> 7.5 ms (forward 3.7 -> 3.0, backward 5.8 -> 4.5), 64^3 2.13 -> 1.55 ms.
+    // The multi-GPU lists keep the (depth, node) order (only the CPU replay has seen them sorted).
+    const char* est_env = getenv("SPLLT_B200_PIPE_ORDER_EST");
+    if (est_env ? atoi(est_env) != 0 : !multi) {
+      auto below_cost = [&](const PTask& t) {
+        const HNode& nd = A.nodes[t.node];
+        const double rows = t.kind == P_SMALL ? nd.m : t.nrows;
+        return 4.0 + rows * nd.n * 8.0 / 25000.0;       // us: hand-off + streaming at ~25 GB/s per CTA
+      };
+      const double strip_cost = 2.3;
+      auto sort_by = [&](std::vector<PTask>& T, const std::vector<double>& est) {
+        std::vector<int> perm(T.size());
+        std::iota(perm.begin(), perm.end(), 0);
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return est[a] < est[b]; });
+        std::vector<PTask> out;
+        out.reserve(T.size());
+        for (int k : perm) out.push_back(T[k]);
+        T.swap(out);
+      };
+      {   // forward: a strip starts after the previous strip of its node and after every contribution
+        std::vector<double> est(TF.size(), 0.0), contrib(strip, 0.0), strip_end(strip, 0.0), last_start(nn, 0.0);
+        for (size_t k = 0; k < TF.size(); ++k) {
+          const PTask& t = TF[k];
+          const PNode& pn = A.pnodes[t.node];
+          if (t.kind == P_DIAG) {
+            const int sidx = pn.strip0 + t.r0;
+            est[k] = std::max(contrib[sidx], t.r0 > 0 ? strip_end[sidx - 1] : 0.0);
+            strip_end[sidx] = est[k] + strip_cost;
+            last_start[t.node] = est[k];
+          } else {
+            double e0;
+            if (t.kind == P_SMALL) e0 = contrib[pn.strip0];
+            else e0 = last_start[t.node] + 0.01;           // behind ALL strip tasks of its node in the list
+            est[k] = e0;
+            const double end = (t.kind == P_SMALL ? e0 : std::max(e0, strip_end[pn.strip0 + pn.np - 1])) + below_cost(t);
+            for (int q = 0; q < t.dest_count; ++q) {
+              const int d = A.pipe_dest[t.dest_begin + q];
+              contrib[d] = std::max(contrib[d], end);
+            }
+          }
+        }
+        sort_by(TF, est);
+      }
+      {   // backward: a below task starts when the ancestor strips it reads are published, the last
+          // strip of a node after all its below tasks, strip i after strip i + 1
+        std::vector<double> est(TB.size(), 0.0), strip_end(strip, 0.0), below_end(nn, 0.0);
+        for (size_t k = 0; k < TB.size(); ++k) {
+          const PTask& t = TB[k];
+          const PNode& pn = A.pnodes[t.node];
+          if (t.kind == P_DIAG) {
+            const int sidx = pn.strip0 + t.r0;
+            est[k] = t.r0 == pn.np - 1 ? below_end[t.node] : strip_end[sidx + 1];
+            strip_end[sidx] = est[k] + strip_cost;
+          } else {
+            double e0 = 0.0;
+            for (int q = 0; q < t.dest_count; ++q) e0 = std::max(e0, strip_end[A.pipe_dest[t.dest_begin + q]]);
+            est[k] = e0;
+            const double end = e0 + below_cost(t);
+            if (t.kind == P_SMALL) strip_end[pn.strip0] = end;
+            else below_end[t.node] = std::max(below_end[t.node], end);
+          }
+        }
+        sort_by(TB, est);
+      }
+    } else {
     // Readiness order (default on one GPU; SPLLT_B200_PIPE_BWD_EARLY=0 / 1 forces it off / on).  Backward, a BELOW task only
     // needs the x of the ancestor strips its rows map to -- usually long before its node's turn in the
     // list.  Claimed at its node's position it would find its inputs ready, but the task trace shows
@@ -1142,6 +1215,7 @@ static void build_pipe_schedule(Analysis& A) {
       sorted.reserve(TB.size());
       for (int k : perm) sorted.push_back(TB[k]);
       TB.swap(sorted);
+    }
     }
   }
   // multi-GPU: pivot columns this rank keeps when the work vector is summed over the ranks
