@@ -360,3 +360,31 @@ def test_multi_gpu_lists_replayed_numerically(world):
     ok, err = chkerr(n, ptr, row, val, np.asfortranarray(x), b)
     assert ok == 1 and err.max() <= 1e-14, err
     assert np.abs(x - xs).max() <= 1e-10
+
+
+ORDERS = {
+    "depth-node": {"SPLLT_B200_PIPE_ORDER_EST": "0", "SPLLT_B200_PIPE_BWD_EARLY": "0"},
+    "backward-readiness": {"SPLLT_B200_PIPE_ORDER_EST": "0", "SPLLT_B200_PIPE_BWD_EARLY": "1"},
+    "earliest-start": {"SPLLT_B200_PIPE_ORDER_EST": "1"},
+}
+
+
+@pytest.mark.parametrize("order", sorted(ORDERS))
+@pytest.mark.parametrize("case", [SMALL[8], SMALL[11], MEDIUM[1], EXTRA[1]], ids=ids([SMALL[8], SMALL[11], MEDIUM[1], EXTRA[1]]))
+def test_every_list_order_is_topological_and_exact(case, order, monkeypatch):
+    """The three orders of the task lists -- (depth, node), backward BELOW tasks behind the last strip
+    they read, and the earliest-start order that is the default on one GPU -- all pass the replay (no
+    task waits on a later one, counters exact, rows covered once) and give the same solution."""
+    for k, v in ORDERS[order].items():
+        monkeypatch.setenv(k, v)
+    test_lists_are_topological_and_cover(case)
+    test_lists_replayed_numerically(case)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_lists_in_earliest_start_order(world, monkeypatch):
+    """the per-rank lists (own subtrees / upper tree) sorted the same way stay valid (not the default yet)"""
+    monkeypatch.setenv("SPLLT_B200_PIPE_ORDER_EST", "1")
+    test_multi_gpu_lists(world)
+    if world == 2:
+        test_multi_gpu_lists_replayed_numerically(world)
