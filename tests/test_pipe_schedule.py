@@ -388,3 +388,9 @@ def test_multi_gpu_lists_in_earliest_start_order(world, monkeypatch):
     test_multi_gpu_lists(world)
     if world == 2:
         test_multi_gpu_lists_replayed_numerically(world)
+
+
+def test_full_size_lists_replay_p3d64():
+    """BASELINE configs[1] (Poisson 64^3, nb = 512): the earliest-start ordered lists of the size the GPU
+    runs (20 000+ tasks) pass the same replay -- no task ever waits on a later one."""
+    test_lists_are_topological_and_cover(("p3d-64-nb512", lambda: M.poisson3d(64), 512, 1, 1))
