@@ -564,8 +564,9 @@ int spllt_b200_pivot_flag(void* fkeep) {
 
 long long spllt_b200_factor_launches(void* fkeep) {
   const Analysis& A = *EE(fkeep)->A;
-  // + assemble + inversion of the diagonal blocks (the memsets are not kernels of ours)
-  return (long long)A.launches.size() + 2;
+  // + epoch counter + assemble + inversion of the diagonal blocks (the memsets are not kernels of ours);
+  // multi-GPU: + two rank barriers + one apply kernel per generated element of this rank
+  return (long long)A.launches.size() + 3 + (A.world > 1 ? 2 + (long long)A.gen.size() : 0);
 }
 long long spllt_b200_solve_launches(void* fkeep, int job) {
   // kernels of one solve with a single right-hand side (the pipelined path when it is enabled)
