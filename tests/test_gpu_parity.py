@@ -323,7 +323,10 @@ def test_schedule_variants(case, env, monkeypatch):
     {"SPLLT_B200_SOLVE_CUT": "2", "SPLLT_B200_PIPE_MAX_NRHS": "8"},
     {"SPLLT_B200_SOLVE_CUT": "5", "SPLLT_B200_GRAPH": "0", "SPLLT_B200_PIPE_MAX_NRHS": "8"},
     {"SPLLT_B200_PIPE_MAX_NRHS": "8", "SPLLT_B200_PIPE_MODE": "96"},
-], ids=["auto", "pipelined", "levelset", "cut2", "cut5-nograph", "pipelined-flags-only"])
+    {"SPLLT_B200_PIPE_MAX_NRHS": "8", "SPLLT_B200_PIPE_ORDER_EST": "0"},
+    {"SPLLT_B200_PIPE_MAX_NRHS": "8", "SPLLT_B200_PIPE_ORDER_EST": "0", "SPLLT_B200_PIPE_BWD_EARLY": "0"},
+], ids=["auto", "pipelined", "levelset", "cut2", "cut5-nograph", "pipelined-flags-only",
+        "pipelined-backward-readiness-order", "pipelined-depth-node-order"])
 @pytest.mark.parametrize("case", [SMALL[7], SMALL[11], MEDIUM[1], MEDIUM[2], MEDIUM[3]],
                          ids=ids([SMALL[7], SMALL[11], MEDIUM[1], MEDIUM[2], MEDIUM[3]]))
 @pytest.mark.parametrize("nrhs", [1, 6])
